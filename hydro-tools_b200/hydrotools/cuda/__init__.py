@@ -1,0 +1,21 @@
+"""hydrotools.cuda -- B200-native (sm_100a) drop-in for the raster-hydrology hot
+path of bluegeo/hydro-tools:
+
+* ``flow_direction_accumulation`` / ``FlowAccumulation``
+  (/root/reference/src/hydrotools/watershed.py:30-75, 321-409)
+* ``slope`` / ``aspect`` / ``terrain_ruggedness_index``
+  (/root/reference/src/hydrotools/elevation.py:24-56, 59-80, 106-128)
+
+Python host code over a C-ABI shared library of hand-written CUDA kernels
+(include/hydrotools_b200.h).  No CPU fallback: importing this package without
+the built library, or calling it without a CUDA device, raises.
+"""
+from . import _native  # noqa: F401  (raises ImportError if the .so is missing)
+from .elevation import slope, aspect, terrain_ruggedness_index, terrain  # noqa: F401
+
+__all__ = [
+    "slope",
+    "aspect",
+    "terrain_ruggedness_index",
+    "terrain",
+]

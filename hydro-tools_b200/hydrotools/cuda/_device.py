@@ -1,0 +1,72 @@
+"""Device-buffer plumbing (torch is used for HBM allocation, streams and
+pinned host memory only; all arithmetic is in the sm_100a kernels)."""
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "hydrotools.cuda needs an NVIDIA B200 (sm_100a); CUDA is not available "
+            "and there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def empty_padded(rows: int, cols: int, dtype: torch.dtype, device, align_elems: int,
+                 extra_top: int = 0, extra_bot: int = 0) -> Tuple[torch.Tensor, int]:
+    """(rows+extra) x ld buffer whose pitch is a multiple of `align_elems`
+    elements; returns (full buffer, ld)."""
+    ld = max(round_up(cols, align_elems), align_elems)
+    buf = torch.empty((rows + extra_top + extra_bot, ld), dtype=dtype, device=device)
+    return buf, ld
+
+
+def as_2d(a: ArrayLike) -> ArrayLike:
+    if a.ndim == 3 and a.shape[0] == 1:
+        a = a[0]
+    if a.ndim != 2:
+        raise ValueError(f"expected a (rows, cols) or (1, rows, cols) raster, got {tuple(a.shape)}")
+    return a
+
+
+def upload(a: ArrayLike, dtype: torch.dtype, align_elems: int, device,
+           extra_top: int = 0, extra_bot: int = 0) -> Tuple[torch.Tensor, int]:
+    """Copy a host (numpy) or device (torch) raster into a pitch-aligned HBM
+    buffer.  Host arrays go through pinned memory, asynchronously."""
+    a = as_2d(a)
+    rows, cols = int(a.shape[0]), int(a.shape[1])
+    buf, ld = empty_padded(rows, cols, dtype, device, align_elems, extra_top, extra_bot)
+    view = buf[extra_top:extra_top + rows, :cols]
+    if isinstance(a, torch.Tensor):
+        view.copy_(a.to(dtype=dtype), non_blocking=True)
+    else:
+        arr = np.ascontiguousarray(np.ma.getdata(a))
+        t = torch.from_numpy(arr)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        view.copy_(t.pin_memory(), non_blocking=True)
+    return buf, ld
+
+
+def download(view: torch.Tensor) -> np.ndarray:
+    """Device -> pinned host -> numpy (synchronises the current stream)."""
+    host = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
+    host.copy_(view, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy().copy()
+
+
+def nodata_args(nodata: Optional[float]) -> Tuple[int, float]:
+    return (0, 0.0) if nodata is None else (1, float(nodata))

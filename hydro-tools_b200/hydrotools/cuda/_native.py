@@ -1,0 +1,71 @@
+"""ctypes binding of libhydrotools_b200.so (C-ABI: include/hydrotools_b200.h).
+
+There is NO CPU fallback: if the shared library is missing this module raises
+at import, and every compute entry point raises if CUDA is unavailable.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libhydrotools_b200.so")
+
+HT_TERRAIN_NODATA = -9999.0
+
+DIR_CODE = 0x0F
+DIR_NEG = 0x10
+DIR_EDGE = 0x20
+DIR_TAINT = 0x40
+DIR_NULL = 0x80
+
+
+class NativeError(RuntimeError):
+    """Non-zero return from the C-ABI."""
+
+
+if not os.path.isfile(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python hydro-tools_b200/build.py` "
+        "(nvcc, sm_100a). hydrotools.cuda has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+_f32 = C.c_float
+_f64 = C.c_double
+_u64 = C.c_uint64
+
+lib.ht_version.restype = _int
+lib.ht_error_string.restype = C.c_char_p
+lib.ht_error_string.argtypes = [_int]
+
+SIGNATURES = {
+    "ht_terrain_fused_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _f64, _int,
+                             _p, _p, _p, _i64, _int, _int, _p],
+    "ht_synth_dem_f32": [_p, _i64, _i64, _i64, _u64, _i64, _i64, _int, _f32, _p],
+    "ht_synth_weight_f32": [_p, _i64, _i64, _i64, _u64, _i64, _p],
+}
+
+
+def _declare():
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _int
+
+
+_declare()
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = lib.ht_error_string(rc).decode()
+    if rc in (-1, -2):
+        raise ValueError(f"{what}: {msg} (code {rc})")
+    raise NativeError(f"{what}: {msg} (code {rc})")
+
+
+def call(name: str, *args):
+    check(getattr(lib, name)(*args), name)

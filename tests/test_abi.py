@@ -1,0 +1,63 @@
+"""CPU: the C-ABI shared library loads (no GPU needed) and exports every entry
+point include/hydrotools_b200.h declares; the host layer fails loudly without a
+device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hydrotools_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ht_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(hc):
+    from hydrotools.cuda import _native
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 5
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert lib.ht_version() >= 100
+
+
+def test_every_bound_symbol_is_declared(hc):
+    from hydrotools.cuda import _native
+    names = set(declared_symbols())
+    for n in _native.SIGNATURES:
+        assert n in names
+
+
+def test_error_strings(hc):
+    from hydrotools.cuda import _native
+    assert _native.lib.ht_error_string(0) == b"ok"
+    assert b"align" in _native.lib.ht_error_string(-2)
+    with pytest.raises(ValueError):
+        _native.check(-1, "x")
+    with pytest.raises(_native.NativeError):
+        _native.check(-3, "x")
+
+
+def test_no_cpu_fallback(hc):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hc.terrain(np.zeros((8, 8), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hydro-tools_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "oracle/" not in src.replace(
+                    "oracle/gdaldem.c", "").replace("oracle/rwatershed.c", "").replace(
+                    "oracle/flowacc.c", ""), f
