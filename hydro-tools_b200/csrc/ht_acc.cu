@@ -1,0 +1,611 @@
+// ht_acc.cu -- flow accumulation over a D8 direction grid.
+//
+// Replaces the accumulation half of GRASS `r.watershed -s [-a]`
+// (/root/reference/src/hydrotools/watershed.py:64-75, accumulation="fa"; rule R5
+// of oracle/rwatershed.c) and GRASS `r.flowaccumulation [weight=]`
+// (/root/reference/src/hydrotools/watershed.py:341-382; oracle/flowacc.c):
+//     acc(c) = w(c) + sum of acc(u) over cells u whose receiver is c.
+//
+// Three stages, all on the device (Barnes-style tile decomposition):
+//  A  acc_tile_kernel<LOCAL>: per 64x64 tile held in shared memory, count
+//     remaining donors per cell and propagate in topological order: a thread
+//     starts at a source, hands its value on with one shared-memory atomic, and
+//     keeps walking for as long as it was the last donor to arrive.  Flow that
+//     leaves the tile is added to the boundary graph (`base`), and every entry
+//     cell records where its path leaves the tile (`next`).
+//  B  coarse_resolve_kernel: the boundary graph (one slot per tile-perimeter
+//     cell) is a forest; subtree sums by pointer doubling, iterated inside one
+//     cooperative launch until no pointer changes.
+//  C  acc_tile_kernel<FINAL>: stage A again with the resolved inflow added at
+//     the entry cells; writes the accumulation (fp64, exact integers for counts)
+//     and the final GRASS direction codes.
+// Counts are carried as u64; weighted sums as fp64 gathered in a fixed
+// neighbour order (no floating-point atomics inside a tile => reproducible).
+// Algorithmic traffic: 1 B/cell read + 8 B/cell written (+4 B/cell weights).
+#include <cooperative_groups.h>
+
+#include "ht_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int T = 64;            // tile edge (cells)
+constexpr int RH = T + 2;        // ring tile rows
+constexpr int XO = 16;           // ring tile column of tile column 0: TMA needs the box
+                                 // to start on a 16-byte boundary of the global row
+constexpr int RP = XO + T + 16;  // ring tile pitch = TMA box width in bytes (96)
+constexpr int THREADS = 256;
+constexpr int CPT = T * T / THREADS; // cells per thread
+constexpr int SLOTS = 4 * T;     // boundary-graph slots per tile
+constexpr int32_t TERMINAL = -1;
+
+// dynamic shared memory layout of acc_tile_kernel
+constexpr int SM_EFF = (RH * RP + 127) / 128 * 128;
+constexpr int SM_VAL = 2 * SM_EFF;
+constexpr int SM_PEND = SM_VAL + T * T * 8;
+constexpr int SM_DON = SM_PEND + T * T;
+constexpr int SM_BAR = SM_DON + T * T;
+constexpr int SM_TOTAL = SM_BAR + 16;
+
+enum { W_ONE = 0, W_TAINT = 1, W_F32 = 2 };
+
+struct AccArgs {
+    int64_t rows, cols;       // owned rows, columns
+    int64_t row0, total_rows;
+    int halo_top, halo_bot;   // 0/1: packed row -1 / row `rows` is a neighbour band's
+    int tiles_x, tiles_y;
+    void *base;               // V[nslots]   boundary-graph node weights (stage A out)
+    int32_t *next;            // [nslots]    boundary-graph successor      (stage A out)
+    const void *inflow;       // V[nslots]   resolved inflow               (stage C in)
+    const float *w;           // weights (W_F32)
+    int64_t w_ld;
+    int has_wnd;
+    float wnd;
+    double *acc;
+    int64_t acc_ld;
+    int8_t *dir_out;
+    int64_t dir_ld;
+};
+
+__device__ __forceinline__ int code_dr(int code) { return (int)((0x122210000ULL >> (4 * code)) & 0xF) - 1; }
+__device__ __forceinline__ int code_dc(int code) { return (int)((0x221000120ULL >> (4 * code)) & 0xF) - 1; }
+// GRASS code that points at window cell k (3x3 row-major)
+__device__ __forceinline__ int win2code(int k) { return (int)((0x765804123ULL >> (4 * k)) & 0xF); }
+// r.watershed neighbour order S,N,W,E,NE,SW,SE,NW as window cells
+__device__ __forceinline__ int ct2win(int ct) { return (0x08625317u >> (4 * ct)) & 0xF; }
+
+// slot of the perimeter cell (lr, gc) [band-local row, column]
+__device__ __forceinline__ int64_t slot_of(const AccArgs &p, int64_t lr, int64_t gc)
+{
+    const int ty = (int)(lr / T), tx = (int)(gc / T);
+    const int ly = (int)(lr - (int64_t)ty * T), lx = (int)(gc - (int64_t)tx * T);
+    const int h = (int)min((int64_t)T, p.rows - (int64_t)ty * T);
+    const int wd = (int)min((int64_t)T, p.cols - (int64_t)tx * T);
+    int k;
+    if (ly == 0) k = lx;
+    else if (ly == h - 1) k = T + lx;
+    else if (lx == 0) k = 2 * T + ly;
+    else k = 3 * T + ly; // lx == wd - 1
+    (void)wd;
+    return ((int64_t)ty * p.tiles_x + tx) * SLOTS + k;
+}
+
+// virtual slots for the cells of the neighbouring bands that this band drains into
+__device__ __forceinline__ int64_t vslot_of(const AccArgs &p, bool bottom, int64_t gc)
+{
+    return (int64_t)p.tiles_x * p.tiles_y * SLOTS + (bottom ? p.cols : 0) + gc;
+}
+
+template <typename V> __device__ __forceinline__ void atomic_add_v(V *p, V v);
+template <> __device__ __forceinline__ void atomic_add_v<unsigned long long>(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+template <> __device__ __forceinline__ void atomic_add_v<double>(double *p, double v) { atomicAdd(p, v); }
+
+template <typename V, int WMODE, bool FINAL>
+__global__ void __launch_bounds__(THREADS, 4)
+acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *pk = smem_raw;                                       // packed bytes, tile + ring
+    uint8_t *eff = smem_raw + SM_EFF;                             // effective link 0..8
+    V *val = reinterpret_cast<V *>(smem_raw + SM_VAL);
+    uint32_t *pend32 = reinterpret_cast<uint32_t *>(smem_raw + SM_PEND); // donors still to arrive
+    uint8_t *don = smem_raw + SM_DON;                             // all in-tile donors (bit mask)
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SM_BAR);
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
+
+    if (tid == 0) {
+        ht::mbar_init(&bar, 1);
+        ht::fence_mbar_init();
+        ht::mbar_expect_tx(&bar, RH * RP);
+        ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
+    }
+    __syncthreads();
+    ht::mbar_wait(&bar, 0);
+
+    // a ring-tile cell is usable if it lies in this band (or its halo rows), inside
+    // the raster, and is not NULL
+    auto valid = [&](int yy, int xx) -> bool {
+        const int64_t lr = y0 - 1 + yy, gc = x0 - XO + xx;
+        if (gc < 0 || gc >= p.cols || lr < -(int64_t)p.halo_top || lr >= p.rows + p.halo_bot)
+            return false;
+        return !(pk[yy * RP + xx] & HT_DIR_NULL);
+    };
+
+    // ---- S1: effective link of every cell of tile + ring
+    for (int i = tid; i < RH * RH; i += THREADS) {
+        const int yy = i / RH, xx = i - yy * RH + XO - 1;
+        int link = 0;
+        if (valid(yy, xx)) {
+            const uint8_t b = pk[yy * RP + xx];
+            const int code = b & HT_DIR_CODE;
+            if (!(b & (HT_DIR_NEG | HT_DIR_EDGE)) && code >= 1 && code <= 8) {
+                const int ny = yy + code_dr(code), nx = xx + code_dc(code);
+                if (ny >= 0 && ny < RH && nx >= XO - 1 && nx <= XO + T && valid(ny, nx))
+                    link = code;
+            }
+        }
+        eff[yy * RP + xx] = (uint8_t)link;
+    }
+    __syncthreads();
+
+    // ---- S2: donor masks, initial values
+    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
+    unsigned src_mask = 0; // which of my CPT cells are sources
+#pragma unroll 4
+    for (int i = 0; i < CPT; i++) {
+        const int c = tid + i * THREADS;
+        const int ly = c / T, lx = c - ly * T;
+        const int yy = ly + 1, xx = lx + XO;
+        unsigned m_in = 0;
+        const bool ok = ly < th && lx < tw && valid(yy, xx);
+        V v = 0;
+        if (ok) {
+#pragma unroll
+            for (int kk = 0; kk < 9; kk++) {
+                if (kk == 4)
+                    continue;
+                const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
+                const bool pts = eff[ny * RP + nx] == win2code(8 - kk);
+                const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
+                if (pts && in_tile)
+                    m_in |= 1u << (kk < 4 ? kk : kk - 1);
+            }
+            if (WMODE == W_ONE)
+                v = 1;
+            else if (WMODE == W_TAINT)
+                v = (pk[yy * RP + xx] & HT_DIR_TAINT) ? 1 : 0;
+            else {
+                const float wv = p.w[(y0 + ly) * p.w_ld + x0 + lx];
+                v = ((p.has_wnd && wv == p.wnd) || wv != wv) ? (V)0 : (V)wv;
+            }
+            if (FINAL && (ly == 0 || ly == th - 1 || lx == 0 || lx == tw - 1))
+                v += reinterpret_cast<const V *>(p.inflow)[slot_of(p, y0 + ly, x0 + lx)];
+            if (m_in == 0)
+                src_mask |= 1u << i;
+        }
+        don[c] = (uint8_t)m_in;
+        reinterpret_cast<uint8_t *>(pend32)[c] = (uint8_t)m_in;
+        val[c] = v;
+    }
+    __syncthreads();
+
+    // ---- S3: topological propagation (chain following)
+    for (int i = 0; i < CPT; i++) {
+        if (!((src_mask >> i) & 1u))
+            continue;
+        int cur = tid + i * THREADS;
+        V v = val[cur];
+        for (;;) {
+            const int ly = cur / T, lx = cur - ly * T;
+            const int link = eff[(ly + 1) * RP + lx + XO];
+            if (!link)
+                break;
+            const int dr = code_dr(link), dc = code_dc(link);
+            const int ny = ly + dr, nx = lx + dc;
+            if (ny < 0 || ny >= th || nx < 0 || nx >= tw) {
+                if (!FINAL) { // flow leaves the tile: feed the boundary graph
+                    const int64_t lr = y0 + ny, gc = x0 + nx;
+                    const int64_t s = lr < 0 ? vslot_of(p, false, gc)
+                                    : lr >= p.rows ? vslot_of(p, true, gc)
+                                                   : slot_of(p, lr, gc);
+                    atomic_add_v(reinterpret_cast<V *>(p.base) + s, v);
+                }
+                break;
+            }
+            const int rc = ny * T + nx;
+            const int kme = (1 - dr) * 3 + (1 - dc); // me, seen from the receiver
+            const unsigned bit = 1u << (kme < 4 ? kme : kme - 1);
+            const int sh = 8 * (rc & 3);
+            __threadfence_block();
+            const unsigned old = atomicAnd(&pend32[rc >> 2], ~(bit << sh));
+            if (((old >> sh) & 0xFFu) != bit)
+                break; // other donors still to come; the last one continues
+            __threadfence_block();
+            // gather in fixed neighbour order: own weight + all donors
+            V sum = val[rc];
+            unsigned m = don[rc];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int kk = b < 4 ? b : b + 1;
+                sum += val[rc + (kk / 3 - 1) * T + (kk % 3 - 1)];
+            }
+            val[rc] = sum;
+            v = sum;
+            cur = rc;
+        }
+    }
+    __syncthreads();
+
+    if (!FINAL) {
+        // ---- S4a: where does the path of each entry cell leave the tile?
+        // perimeter cell index k -> (ly, lx)
+        for (int k = tid; k < SLOTS; k += THREADS) {
+            int ly, lx;
+            if (k < T) { ly = 0; lx = k; }
+            else if (k < 2 * T) { ly = th - 1; lx = k - T; }
+            else if (k < 3 * T) { ly = k - 2 * T; lx = 0; }
+            else { ly = k - 3 * T; lx = tw - 1; }
+            if (ly >= th || lx >= tw)
+                continue;
+            // each perimeter cell has exactly one slot: skip duplicates of corners
+            // and of 1-cell-thick tiles
+            if (k >= T && k < 2 * T && th == 1) continue;
+            if (k >= 2 * T && (ly == 0 || ly == th - 1)) continue;
+            if (k >= 3 * T && tw == 1) continue;
+            const int yy = ly + 1, xx = lx + XO;
+            if (!valid(yy, xx))
+                continue;
+            bool entry = false;
+#pragma unroll
+            for (int kk = 0; kk < 9; kk++) {
+                if (kk == 4)
+                    continue;
+                const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
+                const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
+                entry |= !in_tile && eff[ny * RP + nx] == win2code(8 - kk);
+            }
+            if (!entry)
+                continue;
+            int32_t nxt = TERMINAL;
+            int cy = ly, cx = lx;
+            for (;;) {
+                const int link = eff[(cy + 1) * RP + cx + XO];
+                if (!link)
+                    break;
+                const int ny = cy + code_dr(link), nx = cx + code_dc(link);
+                if (ny < 0 || ny >= th || nx < 0 || nx >= tw) {
+                    const int64_t lr = y0 + ny, gc = x0 + nx;
+                    nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
+                                  : lr >= p.rows ? vslot_of(p, true, gc)
+                                                 : slot_of(p, lr, gc));
+                    break;
+                }
+                cy = ny;
+                cx = nx;
+            }
+            p.next[slot_of(p, y0 + ly, x0 + lx)] = nxt;
+        }
+    }
+    else {
+        // ---- S4b: write accumulation and final direction codes, row-coalesced
+        for (int c = tid; c < T * T; c += THREADS) {
+            const int ly = c / T, lx = c - ly * T;
+            if (ly >= th || lx >= tw)
+                continue;
+            const int yy = ly + 1, xx = lx + XO;
+            const uint8_t b = pk[yy * RP + xx];
+            const bool null = b & HT_DIR_NULL;
+            const double a = (double)val[c];
+            if (p.acc)
+                p.acc[(y0 + ly) * p.acc_ld + x0 + lx] = null ? __longlong_as_double(0x7ff8000000000000LL) : a;
+            if (p.dir_out) {
+                int code = b & HT_DIR_CODE;
+                int out;
+                if (null)
+                    out = -128;
+                else if (b & HT_DIR_NEG)
+                    out = -code;
+                else if ((b & HT_DIR_EDGE) && a >= 60.0) {
+                    // rule R5: an edge cell that is a swale (|acc| >= 60) gets its
+                    // outward code back: first neighbour outside the raster / NULL
+                    // in the order S,N,W,E,NE,SW,SE,NW
+                    out = 0;
+#pragma unroll
+                    for (int ct = 7; ct >= 0; ct--) {
+                        const int kk = ct2win(ct);
+                        const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
+                        const int64_t gr = p.row0 + y0 - 1 + ny, gc = x0 - XO + nx;
+                        const bool outside = gr < 0 || gr >= p.total_rows || gc < 0 || gc >= p.cols;
+                        if (outside || (pk[ny * RP + nx] & HT_DIR_NULL))
+                            out = -win2code(kk);
+                    }
+                    if (out == 0)
+                        out = code; // not an edge after all (foreign packed grid)
+                }
+                else
+                    out = code;
+                p.dir_out[(y0 + ly) * p.dir_ld + x0 + lx] = (int8_t)out;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage B: boundary-graph resolve (subtree sums over a forest) by pointer doubling
+// ---------------------------------------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(256)
+coarse_resolve_kernel(V *aggA, V *aggB, int32_t *ptrA, int32_t *ptrB, int32_t *rootA,
+                      int32_t *rootB, int64_t n, int *flags, int *rounds_out)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int round = 0;
+    for (;; round++) {
+        // agg_{k+1} starts as agg_k
+        for (int64_t u = t0; u < n; u += stride)
+            aggB[u] = aggA[u];
+        grid.sync();
+        bool any = false;
+        for (int64_t u = t0; u < n; u += stride) {
+            const int32_t q = ptrA[u];
+            if (q >= 0) {
+                const V a = aggA[u];
+                if (a != (V)0)
+                    atomic_add_v(&aggB[q], a);
+                ptrB[u] = ptrA[q];
+                if (rootA)
+                    rootB[u] = rootA[q];
+                any = true;
+            }
+            else {
+                ptrB[u] = q;
+                if (rootA)
+                    rootB[u] = rootA[u];
+            }
+        }
+        if (any)
+            flags[round] = 1;
+        grid.sync();
+        V *ta = aggA; aggA = aggB; aggB = ta;
+        int32_t *tp = ptrA; ptrA = ptrB; ptrB = tp;
+        tp = rootA; rootA = rootB; rootB = tp;
+        if (!flags[round] || round == 62)
+            break;
+    }
+    // round + 1 rounds were run; an odd count leaves the result in the caller's "B"
+    // buffers already, an even count leaves it in "A"
+    if (round & 1) {
+        for (int64_t u = t0; u < n; u += stride) {
+            aggB[u] = aggA[u];
+            if (rootA)
+                rootB[u] = rootA[u];
+        }
+    }
+    if (t0 == 0 && rounds_out)
+        *rounds_out = round + 1;
+}
+
+template <typename V>
+__global__ void init_root_kernel(int32_t *root, int64_t n)
+{
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n;
+         u += (int64_t)gridDim.x * blockDim.x)
+        root[u] = (int32_t)u;
+}
+
+struct Workspace {
+    void *aggA, *aggB;
+    int32_t *ptrA, *ptrB, *rootA, *rootB;
+    int *flags;
+    int64_t nslots;
+};
+
+size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
+
+int64_t nslots_of(int64_t rows, int64_t cols)
+{
+    return (int64_t)ht::cdiv(rows, T) * ht::cdiv(cols, T) * SLOTS + 2 * cols;
+}
+
+size_t workspace_bytes(int64_t rows, int64_t cols)
+{
+    const int64_t n = nslots_of(rows, cols);
+    return 2 * align_up(n * 8) + 4 * align_up(n * 4) + align_up(64 * sizeof(int)) + 256;
+}
+
+int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
+{
+    if (!ws || ws_bytes < workspace_bytes(rows, cols))
+        return HT_ERR_WORKSPACE;
+    const int64_t n = nslots_of(rows, cols);
+    uint8_t *b = (uint8_t *)(((uintptr_t)ws + 255) / 256 * 256);
+    w.aggA = b; b += align_up(n * 8);
+    w.aggB = b; b += align_up(n * 8);
+    w.ptrA = (int32_t *)b; b += align_up(n * 4);
+    w.ptrB = (int32_t *)b; b += align_up(n * 4);
+    w.rootA = (int32_t *)b; b += align_up(n * 4);
+    w.rootB = (int32_t *)b; b += align_up(n * 4);
+    w.flags = (int *)b;
+    w.nslots = n;
+    return 0;
+}
+
+int make_packed_map(CUtensorMap &map, const uint8_t *packed, int64_t packed_ld, int64_t rows,
+                    int64_t cols, int halo_top, int halo_bot)
+{
+    const uint8_t *base = packed - (int64_t)halo_top * packed_ld;
+    return ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base,
+                           rows + halo_top + halo_bot, cols, packed_ld, RP, RH, false);
+}
+
+template <typename V, int WMODE, bool FINAL>
+int launch_tile(const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
+{
+    auto kern = acc_tile_kernel<V, WMODE, FINAL>;
+    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    kern<<<p.tiles_x * p.tiles_y, THREADS, SM_TOTAL, st>>>(map, p);
+    HT_LAUNCH_CHECK();
+    return 0;
+}
+
+template <bool FINAL>
+int dispatch_tile(int mode, const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
+{
+    switch (mode) {
+    case W_ONE: return launch_tile<unsigned long long, W_ONE, FINAL>(map, p, st);
+    case W_TAINT: return launch_tile<unsigned long long, W_TAINT, FINAL>(map, p, st);
+    case W_F32: return launch_tile<double, W_F32, FINAL>(map, p, st);
+    }
+    return HT_ERR_ARG;
+}
+
+template <typename V>
+int launch_resolve(Workspace &w, bool with_root, int *rounds_dev, cudaStream_t st)
+{
+    auto kern = coarse_resolve_kernel<V>;
+    int per_sm = 0;
+    HT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    if (per_sm < 1)
+        return HT_ERR_DRIVER;
+    int dev = 0, sms = 0;
+    HT_CUDA_TRY(cudaGetDevice(&dev));
+    HT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int grid = sms * (per_sm > 4 ? 4 : per_sm);
+    const int64_t need = (w.nslots + 255) / 256;
+    if (grid > need)
+        grid = (int)(need > 0 ? need : 1);
+    HT_CUDA_TRY(cudaMemsetAsync(w.flags, 0, 64 * sizeof(int), st));
+    V *aggA = (V *)w.aggA, *aggB = (V *)w.aggB;
+    int32_t *rootA = with_root ? w.rootA : nullptr, *rootB = with_root ? w.rootB : nullptr;
+    if (with_root) {
+        init_root_kernel<V><<<ht::kSMs * 4, 256, 0, st>>>(w.rootA, w.nslots);
+        HT_LAUNCH_CHECK();
+    }
+    int64_t n = w.nslots;
+    void *args[] = {&aggA, &aggB, &w.ptrA, &w.ptrB, &rootA, &rootB, &n, &w.flags, &rounds_dev};
+    HT_CUDA_TRY(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(256), args, 0, st));
+    return 0;
+}
+
+int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t total_rows,
+              int halo_top, int halo_bot)
+{
+    if (rows <= 0 || cols <= 0 || row0 < 0 || total_rows < row0 + rows)
+        return HT_ERR_ARG;
+    if (nslots_of(rows, cols) >= INT32_MAX)
+        return HT_ERR_ARG; // boundary graph is indexed with int32
+    p.rows = rows; p.cols = cols; p.row0 = row0; p.total_rows = total_rows;
+    p.halo_top = halo_top ? 1 : 0; p.halo_bot = halo_bot ? 1 : 0;
+    p.tiles_x = ht::cdiv(cols, T); p.tiles_y = ht::cdiv(rows, T);
+    p.base = nullptr; p.next = nullptr; p.inflow = nullptr;
+    p.w = nullptr; p.w_ld = 0; p.has_wnd = 0; p.wnd = 0.f;
+    p.acc = nullptr; p.acc_ld = 0; p.dir_out = nullptr; p.dir_ld = 0;
+    return 0;
+}
+
+} // namespace
+
+extern "C" size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols)
+{
+    if (rows <= 0 || cols <= 0)
+        return 256;
+    return workspace_bytes(rows, cols);
+}
+
+// Stage A.  After it, the workspace holds the band's boundary graph.
+extern "C" int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows,
+                            int64_t cols, int64_t row0, int64_t total_rows, int halo_top,
+                            int halo_bot, int mode, const float *w, int64_t w_ld, int has_wnd,
+                            float wnd, void *ws, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    AccArgs p;
+    int rc = fill_args(p, rows, cols, row0, total_rows, halo_top, halo_bot);
+    if (rc)
+        return rc;
+    if (!packed || packed_ld < cols || (mode == W_F32 && (!w || w_ld < cols)) || mode < 0 || mode > 2)
+        return HT_ERR_ARG;
+    Workspace wk;
+    if ((rc = carve(ws, ws_bytes, rows, cols, wk)))
+        return rc;
+    CUtensorMap map;
+    if ((rc = make_packed_map(map, packed, packed_ld, rows, cols, p.halo_top, p.halo_bot)))
+        return rc;
+    HT_CUDA_TRY(cudaMemsetAsync(wk.aggA, 0, wk.nslots * 8, st));
+    HT_CUDA_TRY(cudaMemsetAsync(wk.ptrA, 0xFF, wk.nslots * 4, st));
+    p.base = wk.aggA; p.next = wk.ptrA;
+    p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
+    return dispatch_tile<false>(mode, map, p, st);
+}
+
+// Stage B.  Resolved inflow per slot ends up in the workspace ("aggB"); with
+// `want_roots` the last node of every slot's path ("rootB") is kept as well
+// (row-band sharding needs it to build the band-level graph).
+extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roots, void *ws,
+                              size_t ws_bytes, int *rounds_dev, void *stream)
+{
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    if (rc)
+        return rc;
+    if (mode == W_F32)
+        return launch_resolve<double>(wk, want_roots != 0, rounds_dev, (cudaStream_t)stream);
+    return launch_resolve<unsigned long long>(wk, want_roots != 0, rounds_dev, (cudaStream_t)stream);
+}
+
+// Stage C.
+extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows,
+                            int64_t cols, int64_t row0, int64_t total_rows, int halo_top,
+                            int halo_bot, int mode, const float *w, int64_t w_ld, int has_wnd,
+                            float wnd, double *acc, int64_t acc_ld, int8_t *dir_out,
+                            int64_t dir_ld, void *ws, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    AccArgs p;
+    int rc = fill_args(p, rows, cols, row0, total_rows, halo_top, halo_bot);
+    if (rc)
+        return rc;
+    if (!packed || packed_ld < cols || (mode == W_F32 && (!w || w_ld < cols)) || mode < 0 ||
+        mode > 2 || (acc && acc_ld < cols) || (dir_out && dir_ld < cols))
+        return HT_ERR_ARG;
+    Workspace wk;
+    if ((rc = carve(ws, ws_bytes, rows, cols, wk)))
+        return rc;
+    CUtensorMap map;
+    if ((rc = make_packed_map(map, packed, packed_ld, rows, cols, p.halo_top, p.halo_bot)))
+        return rc;
+    p.inflow = wk.aggB;
+    p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
+    p.acc = acc; p.acc_ld = acc_ld; p.dir_out = dir_out; p.dir_ld = dir_ld;
+    return dispatch_tile<true>(mode, map, p, st);
+}
+
+// Stages A + B + C on one device.
+extern "C" int ht_acc_f64(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
+                          int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
+                          double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld,
+                          void *ws, size_t ws_bytes, void *stream)
+{
+    int rc = ht_acc_local(packed, packed_ld, rows, cols, 0, rows, 0, 0, mode, w, w_ld, has_wnd,
+                          wnd, ws, ws_bytes, stream);
+    if (rc)
+        return rc;
+    if ((rc = ht_acc_resolve(rows, cols, mode, 0, ws, ws_bytes, nullptr, stream)))
+        return rc;
+    return ht_acc_final(packed, packed_ld, rows, cols, 0, rows, 0, 0, mode, w, w_ld, has_wnd,
+                        wnd, acc, acc_ld, dir_out, dir_ld, ws, ws_bytes, stream);
+}

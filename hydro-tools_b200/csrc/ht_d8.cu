@@ -1,0 +1,395 @@
+// ht_d8.cu -- D8 single-flow-direction stencil, integer direction codes.
+//
+// Replaces the direction half of GRASS `r.watershed -s` as called by the
+// reference (/root/reference/src/hydrotools/watershed.py:64-75, drainage="fd").
+// On a hydrologically conditioned DEM (pit-free and tie-free after GRASS's
+// round(z*1000) integer scaling -- what BASELINE.json's north_star stipulates)
+// r.watershed's A* pops cells in ascending elevation, so the direction of every
+// cell is a function of its 3x3 window (SURVEY.md 8(c) "local-rule corollary";
+// rules R1-R4 of oracle/rwatershed.c):
+//   * seed (region border, or NULL 8-neighbour): re-pointed at its LOWEST lower
+//     valid neighbour if it has one (and that neighbour's accumulation sign is
+//     tainted), else it keeps the negative outward code;
+//   * other cells: lower neighbours in ascending order; a cardinal is taken at
+//     once, a diagonal unless the flanking cardinal that is still unworked gives
+//     a steeper slope (double arithmetic as in GRASS, behind an fp32 filter).
+//
+// Kernel: persistent CTAs, 2-stage TMA pipeline of (32+4) x (128+8) fp32 tiles
+// (2-cell halo: the taint flag of a cell needs its neighbours' directions).
+// Pass 0 converts the tile in place to GRASS integer millimetres, pass 1
+// computes the packed direction byte of the (32+2) x (128+2) inner cells into
+// shared memory, pass 2 adds the taint flag and writes 128-bit rows.
+// 4 B read + 1 B written per cell (5 B/cell algorithmic).
+#include "ht_common.cuh"
+
+namespace {
+
+constexpr int TW = 128, TH = 32;
+constexpr int PADL = 4;
+constexpr int BW = TW + 2 * PADL; // 136
+constexpr int BH = TH + 4;        // 36
+constexpr int STAGES = 2;
+constexpr int THREADS = 256;
+constexpr uint32_t STAGE_BYTES = BW * BH * 4;
+constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+constexpr int DW = TW + 2, DH = TH + 2; // cells whose direction is computed
+constexpr int DP = 136;                 // pitch of the direction byte tile
+constexpr int32_t INVALID = INT32_MIN;  // NULL or outside the region
+
+struct D8Args {
+    int64_t rows, cols;       // owned rows, columns
+    int64_t row0, total_rows; // position of owned row 0 in the whole raster
+    int halo_top, halo_bot;   // rows available above / below (0 or >= 2)
+    int tiles_x, tiles_y;
+    int has_nodata;
+    float nodata;
+    double ew, ns, diag;
+    float inv_ew, inv_ns, inv_diag;
+    uint8_t *packed;
+    int64_t packed_ld;
+    unsigned long long *counters; // [0] pits, [1] ties (validation only)
+};
+
+// window index (row-major 3x3) of r.watershed's neighbour order S,N,W,E,NE,SW,SE,NW
+// = {7, 1, 3, 5, 2, 6, 8, 0}, as a nibble table so it folds after unrolling
+__device__ __forceinline__ int ct2win(int ct) { return (0x08625317u >> (4 * ct)) & 0xF; }
+// GRASS direction code that points at window cell k = {3, 2, 1, 4, 0, 8, 5, 6, 7}
+__device__ __forceinline__ int win2code(int k) { return (int)((0x765804123ULL >> (4 * k)) & 0xF); }
+
+// rule R1: (int)(z*1000 +- 0.5) in double, as GRASS ele_round()
+__device__ __forceinline__ int32_t alt_from_f32(float z)
+{
+    const double d = (double)z * 1000.0;
+    return (int32_t)(d > 0 ? d + 0.5 : d - 0.5);
+}
+
+// is fl(a/da) < fl(b/db) in double?  fp32 filter first (relative slack 1e-6
+// dwarfs the 2e-7 float error), exact GRASS arithmetic only when it is close.
+__device__ __forceinline__ bool slope_less(int32_t a, double da, float inv_da, int32_t b,
+                                           double db, float inv_db)
+{
+    const float x = (float)a * inv_da, y = (float)b * inv_db;
+    if (x < y * 0.999999f)
+        return true;
+    if (x > y * 1.000001f)
+        return false;
+    return (double)a / da < (double)b / db;
+}
+
+// Packed direction byte of one cell from its 3x3 integer window.
+template <bool VALIDATE>
+__device__ __forceinline__ uint8_t d8_cell(const int32_t w[9], int64_t gr, int64_t gc,
+                                           const D8Args &p, unsigned &pits, unsigned &ties)
+{
+    const int32_t c = w[4];
+    if (c == INVALID)
+        return HT_DIR_NULL;
+    const bool border = (gr == 0 || gc == 0 || gr == p.total_rows - 1 || gc == p.cols - 1);
+    bool any_invalid = false;
+    int32_t low = c;
+    int low_k = -1;
+#pragma unroll
+    for (int ct = 0; ct < 8; ct++) {
+        const int k = ct2win(ct);
+        const int32_t a = w[k];
+        if (a == INVALID) {
+            any_invalid = true;
+            continue;
+        }
+        if (a < low) {
+            low = a;
+            low_k = k;
+        }
+    }
+    if (VALIDATE) {
+        bool tie = false;
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+#pragma unroll
+            for (int j = i + 1; j < 9; j++)
+                tie |= (w[i] != INVALID && w[i] == w[j]);
+        ties += tie;
+        pits += (!border && !any_invalid && low_k < 0);
+    }
+    if (border || any_invalid) {
+        // rule R2 + the re-pointing half of rule R4
+        if (low_k >= 0)
+            return (uint8_t)(win2code(low_k) | HT_DIR_EDGE);
+        int code;
+        if (border)
+            code = gr == 0 ? 2 : gc == 0 ? 4 : gr == p.total_rows - 1 ? 6 : 8;
+        else {
+            code = 0;
+#pragma unroll
+            for (int ct = 7; ct >= 0; ct--)
+                if (w[ct2win(ct)] == INVALID)
+                    code = win2code(ct2win(ct));
+        }
+        return (uint8_t)(code | HT_DIR_EDGE | HT_DIR_NEG);
+    }
+    if (low_k < 0)
+        return 0; // pit: not a conditioned DEM (ht_d8_validate_conditioned reports it)
+    // rule R4, local form.  lowest lower cardinal neighbour (N,W,E,S = 1,3,5,7)
+    int32_t card = c;
+    int card_k = -1;
+#pragma unroll
+    for (int k = 1; k < 9; k += 2)
+        if (w[k] < card) {
+            card = w[k];
+            card_k = k;
+        }
+    // diagonals below `card`, ascending; first one that is not skipped wins
+    unsigned done = 0;
+    for (int it = 0; it < 4; it++) {
+        int32_t dmin = card;
+        int dk = -1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = q < 2 ? 2 * q : 2 * q + 2; // 0, 2, 6, 8
+            if (!((done >> q) & 1u) && w[k] < dmin) {
+                dmin = w[k];
+                dk = k;
+            }
+        }
+        if (dk < 0)
+            break;
+        // flanking cardinals of the diagonal, seen from the centre: same row
+        // (an ew_res step from the centre) and same column (an ns_res step)
+        const int32_t a_ew = (dk % 3 == 0) ? w[3] : w[5]; // (row 1, column of dk)
+        const int32_t a_ns = dk < 3 ? w[1] : w[7];        // (row of dk, column 1)
+        const int32_t rise = c - dmin;
+        bool skip = false;
+        if (a_ew > dmin && a_ew < c)
+            skip = slope_less(rise, p.diag, p.inv_diag, c - a_ew, p.ew, p.inv_ew);
+        if (!skip && a_ns > dmin && a_ns < c)
+            skip = slope_less(rise, p.diag, p.inv_diag, c - a_ns, p.ns, p.inv_ns);
+        if (!skip)
+            return (uint8_t)win2code(dk);
+        done |= 1u << (dk == 0 ? 0 : dk == 2 ? 1 : dk == 6 ? 2 : 3);
+    }
+    return (uint8_t)win2code(card_k);
+}
+
+template <bool VALIDATE>
+__global__ void __launch_bounds__(THREADS, 2)
+d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[STAGES];
+    __shared__ __align__(16) uint8_t dirs[DH * DP];
+
+    const int tid = threadIdx.x;
+    const int ntiles = p.tiles_x * p.tiles_y;
+    if (tid == 0) {
+        ht::tma_prefetch_desc(&map);
+        for (int s = 0; s < STAGES; s++)
+            ht::mbar_init(&full[s], 1);
+        ht::fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int s) {
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        ht::mbar_expect_tx(&full[s], STAGE_BYTES);
+        ht::tma_load_2d(smem_raw + (size_t)s * STAGE_STRIDE, &map, tx * TW - PADL,
+                        ty * TH - 2 + p.halo_top, &full[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < STAGES; s++) {
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < ntiles)
+                issue(t, s);
+        }
+
+    unsigned pits = 0, ties = 0;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+        const int s = k % STAGES;
+        int32_t *alt = reinterpret_cast<int32_t *>(smem_raw + (size_t)s * STAGE_STRIDE);
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int64_t x0 = (int64_t)tx * TW, y0 = (int64_t)ty * TH;
+        ht::mbar_wait(&full[s], (k / STAGES) & 1);
+
+        // ---- pass 0: float metres -> GRASS integer millimetres, in place
+        for (int i = tid; i < BW * BH; i += THREADS) {
+            const int yy = i / BW, xx = i - yy * BW;
+            const int64_t lr = y0 - 2 + yy, gc = x0 - PADL + xx; // owned-row index
+            const int64_t gr = p.row0 + lr;
+            const float z = __int_as_float(alt[i]);
+            const bool inside = gc >= 0 && gc < p.cols && gr >= 0 && gr < p.total_rows &&
+                                lr >= -(int64_t)p.halo_top && lr < p.rows + p.halo_bot;
+            const bool null = !inside || (p.has_nodata && z == p.nodata) || z != z;
+            alt[i] = null ? INVALID : alt_from_f32(z);
+        }
+        __syncthreads();
+
+        // ---- pass 1: direction byte of the tile and a 1-cell ring around it
+        for (int i = tid; i < DW * DH; i += THREADS) {
+            const int yy = i / DW, xx = i - yy * DW; // dirs coords; alt coords +1,+PADL-1
+            const int32_t *a = alt + (yy + 1) * BW + (xx + PADL - 1);
+            int32_t w[9];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    w[r * 3 + c] = a[(r - 1) * BW + (c - 1)];
+            const int64_t lr = y0 - 1 + yy, gc = x0 - 1 + xx;
+            // only cells of the tile itself are counted by the validation
+            const bool own = yy >= 1 && yy <= TH && xx >= 1 && xx <= TW && lr < p.rows &&
+                             gc < p.cols;
+            unsigned pp = 0, tt = 0;
+            dirs[yy * DP + xx] = d8_cell<VALIDATE>(w, p.row0 + lr, gc, p, pp, tt);
+            if (VALIDATE && own) {
+                pits += pp;
+                ties += tt;
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 2: taint flag (rule R4: the cell an unworked seed is re-pointed
+        // at has its accumulation sign flipped) and 128-bit row stores
+        if (!VALIDATE) {
+            // item -> 16 consecutive cells of one row (8 items per row).  Rows -1 and
+            // `rows` (first halo row of a neighbouring band) are stored too, without
+            // the taint flag, for the accumulation stages' ring.
+            for (int item = tid; item < (TH + 2) * 8; item += THREADS) {
+                const int yy = item >> 3, seg = item & 7;
+                const int64_t lr = y0 - 1 + yy;
+                const bool own = yy >= 1 && yy <= TH && lr < p.rows;
+                const bool halo_row = (lr == -1 && p.halo_top) || (lr == p.rows && p.halo_bot);
+                const int64_t gc = x0 + seg * 16;
+                if (!(own || halo_row) || gc >= p.cols)
+                    continue;
+                uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int xx = 1 + seg * 16 + j;
+                    uint8_t b = dirs[yy * DP + xx];
+                    if (own && !(b & HT_DIR_NULL)) {
+                        bool taint = false;
+#pragma unroll
+                        for (int kk = 0; kk < 9; kk++) {
+                            if (kk == 4)
+                                continue;
+                            const uint8_t u = dirs[(yy + kk / 3 - 1) * DP + (xx + kk % 3 - 1)];
+                            // neighbour at window cell kk points back at me with code
+                            // win2code(8 - kk)
+                            taint |= ((u & (HT_DIR_EDGE | HT_DIR_NEG | HT_DIR_NULL)) == HT_DIR_EDGE) &&
+                                     ((u & HT_DIR_CODE) == win2code(8 - kk));
+                        }
+                        if (taint)
+                            b |= HT_DIR_TAINT;
+                    }
+                    out[j >> 2] |= (uint32_t)b << (8 * (j & 3));
+                }
+                uint8_t *dst = p.packed + lr * p.packed_ld + gc;
+                if (gc + 16 <= p.cols)
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+                else
+                    for (int j = 0; j < 16 && gc + j < p.cols; j++)
+                        dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+
+        ht::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            const int next = tile + STAGES * gridDim.x;
+            if (next < ntiles)
+                issue(next, s);
+        }
+    }
+    if (VALIDATE) {
+        if (pits)
+            atomicAdd(&p.counters[0], (unsigned long long)pits);
+        if (ties)
+            atomicAdd(&p.counters[1], (unsigned long long)ties);
+    }
+}
+
+int setup(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_nodata,
+          float nodata, double ewres, double nsres, int64_t row0, int64_t total_rows,
+          int halo_top, int halo_bot, D8Args &p, CUtensorMap &map)
+{
+    if (!dem || rows <= 0 || cols <= 0 || ld < cols || ewres <= 0.0 || nsres <= 0.0 ||
+        row0 < 0 || total_rows < row0 + rows || halo_top < 0 || halo_bot < 0)
+        return HT_ERR_ARG;
+    // a side without halo rows must be the edge of the whole raster
+    if ((halo_top == 0 && row0 != 0) || (halo_bot == 0 && row0 + rows != total_rows) ||
+        (halo_top != 0 && halo_top < 2 && row0 >= 2) ||
+        (halo_bot != 0 && halo_bot < 2 && total_rows - row0 - rows >= 2))
+        return HT_ERR_ARG;
+    p.rows = rows; p.cols = cols; p.row0 = row0; p.total_rows = total_rows;
+    p.halo_top = halo_top > 2 ? 2 : halo_top;
+    p.halo_bot = halo_bot > 2 ? 2 : halo_bot;
+    p.tiles_x = ht::cdiv(cols, TW); p.tiles_y = ht::cdiv(rows, TH);
+    p.has_nodata = has_nodata ? 1 : 0;
+    p.nodata = nodata;
+    p.ew = ewres; p.ns = nsres; p.diag = sqrt(ewres * ewres + nsres * nsres);
+    p.inv_ew = (float)(1.0 / p.ew); p.inv_ns = (float)(1.0 / p.ns);
+    p.inv_diag = (float)(1.0 / p.diag);
+    p.packed = nullptr; p.packed_ld = 0; p.counters = nullptr;
+    const float *base = dem - (int64_t)p.halo_top * ld;
+    return ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,
+                           rows + p.halo_top + p.halo_bot, cols, ld, BW, BH, true);
+}
+
+template <bool VALIDATE>
+int launch(const CUtensorMap &map, const D8Args &p, cudaStream_t st)
+{
+    auto kern = d8_kernel<VALIDATE>;
+    const size_t smem = (size_t)STAGES * STAGE_STRIDE;
+    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = p.tiles_x * p.tiles_y;
+    int grid = 2 * ht::kSMs;
+    if (grid > ntiles)
+        grid = ntiles;
+    kern<<<grid, THREADS, smem, st>>>(map, p);
+    HT_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace
+
+extern "C" int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld,
+                         int has_nodata, float nodata, double ewres, double nsres,
+                         int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                         uint8_t *packed, int64_t packed_ld, void *stream)
+{
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    D8Args p;
+    CUtensorMap map;
+    int rc = setup(dem, rows, cols, ld, has_nodata, nodata, ewres, nsres, row0, total_rows,
+                   halo_top, halo_bot, p, map);
+    if (rc)
+        return rc;
+    if (!packed || packed_ld < cols)
+        return HT_ERR_ARG;
+    if (((uintptr_t)packed & 15) || (packed_ld & 15))
+        return HT_ERR_ALIGN;
+    p.packed = packed; p.packed_ld = packed_ld;
+    return launch<false>(map, p, (cudaStream_t)stream);
+}
+
+extern "C" int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,
+                                              int64_t ld, int has_nodata, float nodata,
+                                              int64_t row0, int64_t total_rows, int halo_top,
+                                              int halo_bot, unsigned long long *counts2,
+                                              void *stream)
+{
+    if (!counts2)
+        return HT_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    HT_CUDA_TRY(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    D8Args p;
+    CUtensorMap map;
+    int rc = setup(dem, rows, cols, ld, has_nodata, nodata, 1.0, 1.0, row0, total_rows,
+                   halo_top, halo_bot, p, map);
+    if (rc)
+        return rc;
+    p.counters = counts2;
+    return launch<true>(map, p, st);
+}

@@ -12,10 +12,22 @@ the built library, or calling it without a CUDA device, raises.
 """
 from . import _native  # noqa: F401  (raises ImportError if the .so is missing)
 from .elevation import slope, aspect, terrain_ruggedness_index, terrain  # noqa: F401
+from .watershed import (  # noqa: F401
+    FlowAccumulation,
+    flow_accumulation_arrays,
+    flow_direction_accumulation,
+    flow_direction_accumulation_arrays,
+    validate_conditioned,
+)
 
 __all__ = [
     "slope",
     "aspect",
     "terrain_ruggedness_index",
     "terrain",
+    "flow_direction_accumulation",
+    "flow_direction_accumulation_arrays",
+    "FlowAccumulation",
+    "flow_accumulation_arrays",
+    "validate_conditioned",
 ]

@@ -43,6 +43,20 @@ lib.ht_error_string.argtypes = [_int]
 SIGNATURES = {
     "ht_terrain_fused_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _f64, _int,
                              _p, _p, _p, _i64, _int, _int, _p],
+    "ht_d8_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _i64, _i64, _int, _int,
+                  _p, _i64, _p],
+    "ht_d8_validate_conditioned_f32": [_p, _i64, _i64, _i64, _int, _f32, _i64, _i64, _int,
+                                       _int, _p, _p],
+    "ht_dir_pack_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],
+    "ht_dir_unpack_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],
+    "ht_acc_local": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _i64, _int,
+                     _f32, _p, C.c_size_t, _p],
+    "ht_acc_resolve": [_i64, _i64, _int, _int, _p, C.c_size_t, _p, _p],
+    "ht_acc_final": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _i64, _int,
+                     _f32, _p, _i64, _p, _i64, _p, C.c_size_t, _p],
+    "ht_acc_f64": [_p, _i64, _i64, _i64, _int, _p, _i64, _int, _f32, _p, _i64, _p, _i64,
+                   _p, C.c_size_t, _p],
+    "ht_acc_apply_sign": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p],
     "ht_synth_dem_f32": [_p, _i64, _i64, _i64, _u64, _i64, _i64, _int, _f32, _p],
     "ht_synth_weight_f32": [_p, _i64, _i64, _i64, _u64, _i64, _p],
 }
@@ -56,6 +70,10 @@ def _declare():
 
 
 _declare()
+lib.ht_acc_workspace_bytes.argtypes = [_i64, _i64]
+lib.ht_acc_workspace_bytes.restype = C.c_size_t
+
+MODE_COUNT, MODE_TAINT, MODE_WEIGHTED = 0, 1, 2
 
 
 def check(rc: int, what: str):

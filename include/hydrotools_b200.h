@@ -63,6 +63,67 @@ int ht_terrain_fused_f32(const float *dem, int64_t rows, int64_t cols, int64_t l
                          float *slope, float *aspect, float *tri, int64_t out_ld,
                          int halo_top, int halo_bot, void *stream);
 
+/* ---- watershed.flow_direction_accumulation, direction half ------------------
+ * replaces  GRASS r.watershed -s  drainage=fd
+ *   /root/reference/src/hydrotools/watershed.py:64-75 (utils.py:157-159 runs it)
+ * Input must be hydrologically conditioned (pit-free, tie-free after GRASS's
+ * round(z*1000)); ht_d8_validate_conditioned_f32 counts violations.
+ * Needs 2 halo rows per shared side when sharded.  Writes the packed byte of
+ * the owned rows and, when a side has halo rows, of the first halo row beyond it
+ * (packed row -1 / row `rows`), which stage A/C of the accumulation read.
+ * `packed`: 16-B aligned, packed_ld % 16 == 0. */
+int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_nodata,
+              float nodata, double ewres, double nsres, int64_t row0,
+              int64_t total_rows, int halo_top, int halo_bot, uint8_t *packed,
+              int64_t packed_ld, void *stream);
+/* counts2[0] = pits (non-seed cells without a strictly lower neighbour),
+ * counts2[1] = cells whose 3x3 window holds two equal integer elevations */
+int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,
+                                   int64_t ld, int has_nodata, float nodata,
+                                   int64_t row0, int64_t total_rows, int halo_top,
+                                   int halo_bot, unsigned long long *counts2,
+                                   void *stream);
+
+/* GRASS int8 codes (-128 = NULL) <-> packed byte; used for direction rasters that
+ * come from disk (FlowAccumulation(direction),
+ * /root/reference/src/hydrotools/watershed.py:329-339) */
+int ht_dir_pack_i8(const int8_t *dir, int64_t ld, int64_t rows, int64_t cols,
+                   uint8_t *packed, int64_t packed_ld, void *stream);
+int ht_dir_unpack_i8(const uint8_t *packed, int64_t packed_ld, int64_t rows,
+                     int64_t cols, int8_t *dir, int64_t ld, void *stream);
+
+/* ---- accumulation -----------------------------------------------------------
+ * replaces  GRASS r.watershed accumulation=fa [-a]   (watershed.py:64-75)
+ *      and  GRASS r.flowaccumulation [weight=]      (watershed.py:341-382)
+ * mode: 0 = cell count, 1 = count of tainted cells upstream (sign step),
+ *       2 = fp32 weights summed in fp64.
+ * Stage A (ht_acc_local) builds the tile boundary graph in the workspace,
+ * stage B (ht_acc_resolve) resolves it by pointer doubling until no pointer
+ * changes, stage C (ht_acc_final) writes acc (fp64; NaN where NULL) and, if
+ * dir_out != NULL, the final GRASS direction codes (int8, -128 = NULL).
+ * ht_acc_f64 = A + B + C for an unsharded raster. */
+size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols);
+int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
+                 int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                 int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
+                 void *ws, size_t ws_bytes, void *stream);
+int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roots, void *ws,
+                   size_t ws_bytes, int *rounds_dev, void *stream);
+int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
+                 int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                 int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
+                 double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld, void *ws,
+                 size_t ws_bytes, void *stream);
+int ht_acc_f64(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
+               int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
+               double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld, void *ws,
+               size_t ws_bytes, void *stream);
+/* positive_only=False: negate acc at edge cells and below tainted cells
+ * (taint_acc = result of mode 1) */
+int ht_acc_apply_sign(double *acc, int64_t acc_ld, const double *taint_acc,
+                      int64_t taint_ld, const uint8_t *packed, int64_t packed_ld,
+                      int64_t rows, int64_t cols, void *stream);
+
 /* ---- synthetic workloads (BASELINE.json configs 2-5) ----------------------
  * integer-exact fractal DEM / weights, see include/ht_synth.h */
 int ht_synth_dem_f32(float *dem, int64_t rows, int64_t cols, int64_t ld,

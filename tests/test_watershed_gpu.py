@@ -1,0 +1,178 @@
+"""GPU parity: D8 direction codes and cell-count accumulation are BIT-EXACT
+against the r.watershed oracle on hydrologically conditioned DEMs; weighted
+accumulation within 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+ND = -32767.0
+
+
+def check_fd_fa(hc, dem, nodata, csx, csy, positive_only=True):
+    fd, fa = hc.flow_direction_accumulation_arrays(dem, nodata=nodata, csx=csx, csy=csy,
+                                                   positive_only=positive_only)
+    efd, efa = oracle.rwatershed(dem, nodata, csx, csy, positive_only=positive_only)
+    assert fd.dtype == np.int8 and fa.dtype == np.float64
+    np.testing.assert_array_equal(fd, efd)
+    np.testing.assert_array_equal(fa, efa)  # NaN == NaN positions included
+    return fd, fa
+
+
+def test_conditioned_bundled_dem(hc, golden):
+    """configs[0] input, conditioned as north_star stipulates (rank of the oracle's
+    own A* order); committed golden vectors."""
+    nd, res = float(golden["dem_nodata"]), float(golden["res"])
+    cdem = oracle.condition_by_rank(golden["dem"], nd, res, res)
+    fd, fa = check_fd_fa(hc, cdem, nd, res, res)
+    np.testing.assert_array_equal(fd, golden["cfd"])
+    np.testing.assert_array_equal(np.nan_to_num(fa, nan=-1).astype(np.float32),
+                                  np.nan_to_num(golden["cfa"], nan=-1))
+    # sign ("likely underestimate") parity
+    _, signed = check_fd_fa(hc, cdem, nd, res, res, positive_only=False)
+    neg = np.unpackbits(golden["cneg"])[:signed.size].reshape(signed.shape).astype(bool)
+    np.testing.assert_array_equal(signed < 0, neg)
+
+
+def test_bundled_dem_is_refused_unconditioned(hc, golden):
+    nd = float(golden["dem_nodata"])
+    pits, ties = hc.validate_conditioned(golden["dem"], nd)
+    assert (pits, ties) == oracle.check_conditioned(golden["dem"], nd)
+    assert pits == 2326
+    with pytest.raises(ValueError, match="not hydrologically conditioned"):
+        hc.flow_direction_accumulation_arrays(golden["dem"], nodata=nd, csx=5.0, csy=5.0)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (2, 2), (3, 3), (5, 7), (63, 65),
+                                   (64, 64), (65, 129), (130, 70), (200, 300), (257, 513)])
+def test_ragged_shapes(hc, shape):
+    dem = oracle.synth_dem(shape[0] * 7 + shape[1], shape[0], shape[1])
+    assert hc.validate_conditioned(dem) == (0, 0)
+    check_fd_fa(hc, dem, None, 10.0, 10.0)
+    check_fd_fa(hc, dem, None, 10.0, 10.0, positive_only=False)
+
+
+@pytest.mark.parametrize("seed,shape", [(1, (90, 120)), (2, (300, 500)), (3, (700, 333))])
+def test_synthetic_with_nulls(hc, seed, shape):
+    dem = oracle.synth_dem(seed, shape[0], shape[1], with_nulls=True)
+    check_fd_fa(hc, dem, ND, 10.0, 10.0)
+    check_fd_fa(hc, dem, ND, 10.0, 10.0, positive_only=False)
+
+
+def test_anisotropic_cells(hc):
+    """ns_res != ew_res changes the diagonal-skip rule (rule R4)."""
+    dem = oracle.synth_dem(9, 220, 310)
+    check_fd_fa(hc, dem, None, 30.0, 10.0)
+    check_fd_fa(hc, dem, None, 5.0, 12.5)
+
+
+def test_all_null_and_nan_nodata(hc):
+    dem = np.full((40, 50), ND, np.float32)
+    fd, fa = hc.flow_direction_accumulation_arrays(dem, nodata=ND)
+    assert (fd == -128).all() and np.isnan(fa).all()
+    d = oracle.synth_dem(4, 100, 100, with_nulls=True)
+    d[d == ND] = np.nan
+    check_fd_fa(hc, d, None, 10.0, 10.0)
+
+
+def test_medium_synthetic(hc):
+    """6 M cells: many tiles, long rivers through the boundary graph."""
+    dem = oracle.synth_dem(20261019, 2000, 3000)
+    fd, fa = check_fd_fa(hc, dem, None, 10.0, 10.0)
+    assert fa.max() > 1e5
+
+
+def test_size_independent_properties(hc):
+    """At sizes the oracle is too slow for: mass balance of the accumulation."""
+    import torch
+    from hydrotools.cuda import synth
+    n = 4096
+    buf, ld = synth.synth_dem(77, n, n)
+    fd, fa = hc.flow_direction_accumulation_arrays(buf[:, :n], csx=10.0, csy=10.0)
+    fd, fa = fd.cpu().numpy(), fa.cpu().numpy()
+    assert (fd != -128).all() and (fd != 0).all()
+    dr = np.array([0, -1, -1, -1, 0, 1, 1, 1, 0]); dc = np.array([0, 1, 0, -1, -1, -1, 0, 1, 1])
+    r, c = np.indices(fd.shape)
+    edge = (r == 0) | (c == 0) | (r == n - 1) | (c == n - 1)
+    donates = (fd > 0) & ~edge
+    rr, cc = r + dr[np.abs(fd)], c + dc[np.abs(fd)]
+    # every cell's accumulation = 1 + sum of its donors' accumulation
+    inflow = np.zeros_like(fa)
+    np.add.at(inflow, (rr[donates], cc[donates]), fa[donates])
+    np.testing.assert_array_equal(fa, inflow + 1)
+    # all flow ends in edge cells: their accumulations add up to the cell count
+    assert fa[~donates].sum() == n * n
+
+
+# ---------------------------------------------------------------- FlowAccumulation
+def test_flowacc_counts_and_weights(hc, golden):
+    nd, pnd = float(golden["dem_nodata"]), float(golden["precip_nodata"])
+    for fd in (golden["fd"], golden["cfd"]):
+        cnt = hc.flow_accumulation_arrays(fd)
+        np.testing.assert_array_equal(cnt, oracle.flowacc(fd))
+        w = hc.flow_accumulation_arrays(fd, golden["precip"], pnd)
+        e = oracle.flowacc(fd, golden["precip"], pnd)
+        np.testing.assert_array_equal(np.isnan(w), np.isnan(e))
+        m = ~np.isnan(e)
+        np.testing.assert_allclose(w[m], e[m], rtol=1e-5, atol=0)
+
+
+def test_flowacc_synthetic_weighted(hc):
+    dem = oracle.synth_dem(5, 900, 1100, with_nulls=True)
+    fd, _ = oracle.rwatershed(dem, ND, 10.0, 10.0)
+    w = oracle.synth_weight(5, 900, 1100)
+    got = hc.flow_accumulation_arrays(fd, w)
+    exp = oracle.flowacc(fd, w)
+    m = ~np.isnan(exp)
+    np.testing.assert_allclose(got[m], exp[m], rtol=1e-5, atol=0)
+    # fixed gather order inside a tile, atomics only across tiles: run-to-run
+    # differences stay far below the contract
+    again = hc.flow_accumulation_arrays(fd, w)
+    np.testing.assert_allclose(again[m], got[m], rtol=1e-12)
+
+
+def test_misaligned_weight_raises(hc, golden):
+    with pytest.raises(ValueError, match="does not align"):
+        hc.flow_accumulation_arrays(golden["fd"], golden["precip"][:-1])
+
+
+# ---------------------------------------------------------------- signatures / files
+def test_unsupported_modes(hc):
+    with pytest.raises(NotImplementedError):
+        hc.flow_direction_accumulation("a.tif", "b.tif", "c.tif", single=False)
+    with pytest.raises(NotImplementedError):
+        hc.flow_direction_accumulation("a.tif", "b.tif", "c.tif", beautify=True)
+
+
+def test_path_level_api(hc, golden, tmp_path):
+    from hydrotools.cuda import _io
+    from test_terrain_gpu import _write_template
+    nd, res = float(golden["dem_nodata"]), float(golden["res"])
+    cdem = oracle.condition_by_rank(golden["dem"], nd, res, res)
+    tmpl, src = str(tmp_path / "t.tif"), str(tmp_path / "dem.tif")
+    _write_template(tmpl, cdem, nd)
+    _io.write_raster(cdem, tmpl, src, nodata=nd)
+    fdp, fap = str(tmp_path / "fd.tif"), str(tmp_path / "fa.tif")
+    hc.flow_direction_accumulation(src, fdp, fap, memory=4096)
+    fd, m = _io.read_raster(fdp)
+    fa, _ = _io.read_raster(fap)
+    np.testing.assert_array_equal(fd, golden["cfd"])
+    assert m["nodata"] == -128 and fa.dtype == np.float64
+    # FlowAccumulation on the direction raster just written
+    pp = str(tmp_path / "precip.tif")
+    _io.write_raster(golden["precip"], tmpl, pp, nodata=float(golden["precip_nodata"]))
+    facc = hc.FlowAccumulation(fdp)
+    facc.calculate(pp, str(tmp_path / "sum.tif"), "sum")
+    facc.calculate(pp, str(tmp_path / "mean.tif"), "mean")
+    facc.contributing_area(str(tmp_path / "ca.tif"))
+    s, _ = _io.read_raster(str(tmp_path / "sum.tif"))
+    e = oracle.flowacc(golden["cfd"], golden["precip"], float(golden["precip_nodata"]))
+    ok = ~np.isnan(e)
+    np.testing.assert_allclose(s[ok], e[ok], rtol=1e-5)
+    mean, mm = _io.read_raster(str(tmp_path / "mean.tif"))
+    cnt = oracle.flowacc(golden["cfd"])
+    np.testing.assert_allclose(mean[ok], (e[ok] / cnt[ok]).astype(np.float32), rtol=1e-5)
+    ca, _ = _io.read_raster(str(tmp_path / "ca.tif"))
+    np.testing.assert_allclose(ca[ok], cnt[ok] * 25.0 / 1e6, rtol=1e-12)
