@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hydro-tools hot path on B200.
+
+Metric (BASELINE.json): D8 flow direction + cell-count accumulation, Gcells/s.
+A "step" is one pass of the hot path (ht_d8_f32 + ht_acc_local + ht_acc_resolve
++ ht_acc_final) over one synthetic conditioned fractal DEM.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...
+
+N = 1 : BASELINE.json configs[1], 10 000 x 10 000 fp32, whole raster on one GPU.
+N > 1 : the raster is row-band sharded, 10 000 rows per GPU (weak scaling), halo
+        rows and band-boundary flows exchanged through torch.distributed (NCCL).
+`value`  : device-resident (DEM already in HBM), CUDA events, max over ranks.
+`e2e`    : the same work through hydrotools.cuda.flow_direction_accumulation_arrays
+           with pinned HOST buffers, H2D and D2H copies inside the timed region.
+`--impl reference` times the CPU oracle (restatement of GRASS r.watershed, which
+the reference shells out to; single-threaded like GRASS) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "hydro-tools_b200"))
+
+METRIC = "D8 flow-dir+accumulation Gcells/s"
+UNIT = "Gcells/s"
+SEED = 20261019
+ROWS_PER_GPU = 10000
+COLS = 10000
+CSX = CSY = 10.0
+TERRAIN_N = 32768  # configs[2]: fused slope/aspect/TRI
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Polls NVML while the timed region runs (nvidia-smi -lms 200 is too coarse
+    for a region that lasts tens of milliseconds)."""
+
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+        0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+        0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def oracle_sample_gcells(sample_rows, cols, total_rows):
+    import oracle
+    dem = oracle.synth_dem(SEED, sample_rows, cols, row0=0, total_rows=total_rows)
+    t0 = time.perf_counter()
+    oracle.rwatershed(dem, None, CSX, CSY, positive_only=True)
+    dt = time.perf_counter() - t0
+    return sample_rows * cols / dt / 1e9, dt
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement of r.watershed -s -a (GRASS is
+    single-threaded; so is this), each step one bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total_rows = ROWS_PER_GPU * args.gpus
+    # size the sample so that (steps + warmup) samples take about two minutes
+    g, dt = oracle_sample_gcells(500, COLS, total_rows)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    rows = int(max(200, min(2500, 500 * budget / max(dt, 1e-3) * 0.8)))
+    for _ in range(args.warmup):
+        oracle_sample_gcells(rows, COLS, total_rows)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_sample_gcells(rows, COLS, total_rows)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = rows * COLS / dt / 1e9
+    sample = f"first {rows} rows x {COLS} cols of the {total_rows} x {COLS} synthetic DEM per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n):
+    return {
+        "workload": f"synthetic conditioned fractal DEM {ROWS_PER_GPU * n}x{COLS} fp32, "
+                    f"D8 + cell-count accumulation (BASELINE.json configs[1] per GPU)",
+        "rows": ROWS_PER_GPU * n, "cols": COLS, "seed": SEED, "cell_size_m": CSX,
+        "sharding": "whole raster on one GPU" if n == 1 else f"{n} row bands of {ROWS_PER_GPU} rows",
+        "l2": "inputs (400 MB DEM per GPU) exceed the 126 MB L2; no flush between iterations",
+    }
+
+
+# --------------------------------------------------------------------------- product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    import numpy as np
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import hydrotools.cuda as hc
+    from hydrotools.cuda import _native as N, _device as D, synth, watershed as W
+    from hydrotools.cuda import distributed as HD
+
+    peak, peak_kind = measured_peak()
+    dev = torch.device("cuda", local_rank)
+    rows, cols = ROWS_PER_GPU, COLS
+    total_rows = rows * world
+    row0 = rank * rows
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    engine = HD.BandEngine(rank, world, rows, cols, total_rows, CSX, CSY, nodata=None)
+    engine.generate_synthetic(SEED)
+    pits, ties = engine.validate()
+    if pits or ties:
+        raise SystemExit(f"synthetic DEM is not conditioned: {pits} pits, {ties} ties")
+
+    def step():
+        engine.flow_direction_accumulation()
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = engine.launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / max(args.steps, 1)
+    launches = engine.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total_rows * cols / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API: pinned host in, host out
+    e2e = None
+    if world == 1:
+        host_dem = torch.empty((rows, cols), dtype=torch.float32, pin_memory=True)
+        host_dem.copy_(engine.dem_view())
+        out_fd = torch.empty((rows, cols), dtype=torch.int8, pin_memory=True)
+        out_fa = torch.empty((rows, cols), dtype=torch.float64, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            hc.flow_direction_accumulation_arrays(
+                host_dem.numpy(), nodata=None, csx=CSX, csy=CSY, positive_only=True,
+                out_direction=out_fd.numpy(), out_accumulation=out_fa.numpy())
+
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": rows * cols / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": rows * cols * 4, "d2h_bytes_per_step": rows * cols * 9,
+               "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "api": "hydrotools.cuda.flow_direction_accumulation_arrays (validate + D8 + "
+                      "accumulation), pinned host buffers"}
+        # the e2e result must be the same answer
+        fd_dev, fa_dev = engine.results()
+        assert torch.equal(out_fd.to(dev), fd_dev) and torch.equal(out_fa.to(dev), fa_dev)
+
+    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline
+    kernels = engine.time_kernels(iters=max(3, min(args.steps, 10)))
+    cells = rows * cols
+    alg_bytes = {"d8_kernel": 5, "acc_tile_kernel<local>": 1, "coarse_resolve_kernel": 0,
+                 "acc_tile_kernel<final>": 10}
+    for k in kernels:
+        b = alg_bytes.get(k["name"], 0) * cells
+        k["algorithmic_bytes"] = b
+        k["gbs"] = b / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
+        k["frac"] = k["gbs"] / peak
+    dom = max(kernels, key=lambda k: k["ms"])
+    traffic = load_traffic(dom["name"])
+    roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": peak,
+                "peak_kind": f"of {peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic,
+                "share_of_step": dom["ms"] / sum(k["ms"] for k in kernels)}
+
+    stencil = None
+    cpu = None
+    if rank == 0:
+        if world == 1:
+            stencil = terrain_roofline(peak)
+        g, dt = oracle_sample_gcells(2500, COLS, total_rows)
+        cpu = {"value": g, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first 2500 rows x {COLS} cols of the same DEM, oracle/rwatershed.c "
+                         f"(restatement of single-threaded GRASS r.watershed -s -a), {dt:.1f} s",
+               "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "kernels": kernels, "stencil_roofline": stencil,
+            "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic(kernel_name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_name)
+    except Exception:
+        return None
+
+
+def terrain_roofline(peak):
+    """configs[2] on one GPU: fused slope+aspect+TRI on 32768^2, 16 B/cell."""
+    import torch
+    from hydrotools.cuda import _native as N, _device as D, synth
+    n = TERRAIN_N
+    dem, ld = synth.synth_dem(SEED, n, n)
+    outs = [torch.empty((n, ld), dtype=torch.float32, device="cuda") for _ in range(3)]
+    st = D.stream_ptr()
+
+    def run():
+        N.call("ht_terrain_fused_f32", dem.data_ptr(), n, n, ld, 0, 0.0, CSX, CSY, 1.0, 0,
+               outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), ld, 0, 0, st)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gbs = n * n * 16 / (ms * 1e-3) / 1e9
+    del outs, dem
+    torch.cuda.empty_cache()
+    return {"kernel": "terrain_kernel (fused slope+aspect+TRI)", "workload": f"{n}x{n} fp32",
+            "ms": ms, "gcells_s": n * n / (ms * 1e-3) / 1e9, "achieved": gbs, "peak": peak,
+            "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_cell": 16}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@
 // neighbour order (no floating-point atomics inside a tile => reproducible).
 // Algorithmic traffic: 1 B/cell read + 8 B/cell written (+4 B/cell weights).
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "ht_common.cuh"
 
@@ -66,6 +67,10 @@ struct AccArgs {
     int64_t acc_ld;
     int8_t *dir_out;
     int64_t dir_ld;
+    uint16_t *lacc;           // tile-local counts, stage A -> stage C (count modes)
+    int64_t lacc_ld;
+    const uint8_t *packed;    // owned row 0 of the packed grid (rare global look-ups)
+    int64_t packed_ld;
 };
 
 __device__ __forceinline__ int code_dr(int code) { return (int)((0x122210000ULL >> (4 * code)) & 0xF) - 1; }
@@ -97,12 +102,14 @@ __device__ __forceinline__ int64_t vslot_of(const AccArgs &p, bool bottom, int64
     return (int64_t)p.tiles_x * p.tiles_y * SLOTS + (bottom ? p.cols : 0) + gc;
 }
 
+__device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 template <typename V> __device__ __forceinline__ void atomic_add_v(V *p, V v);
 template <> __device__ __forceinline__ void atomic_add_v<unsigned long long>(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 template <> __device__ __forceinline__ void atomic_add_v<double>(double *p, double v) { atomicAdd(p, v); }
 
 template <typename V, int WMODE, bool FINAL>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, 5)
 acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -111,7 +118,9 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     V *val = reinterpret_cast<V *>(smem_raw + SM_VAL);
     uint32_t *pend32 = reinterpret_cast<uint32_t *>(smem_raw + SM_PEND); // donors still to arrive
     uint8_t *don = smem_raw + SM_DON;                             // all in-tile donors (bit mask)
-    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SM_BAR);
+    // the mbarrier sits behind whichever value layout this instantiation uses
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(
+        smem_raw + (std::is_same<V, double>::value ? SM_BAR : SM_VAL + T * T * (FINAL ? 8 : 4)));
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
@@ -153,7 +162,13 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     }
     __syncthreads();
 
-    // ---- S2: donor masks, initial values
+    // ---- S2: donor counts / masks, initial values
+    // counts: one 32-bit word per cell = [donors still to arrive : 4 | low part : 28]
+    // plus (stage C only, where inflow can exceed 2^24) a high word; a value is
+    // hi * 2^24 + lo with lo allowed to run up to 9 * 2^24 unnormalised.
+    constexpr bool CNT = !std::is_same<V, double>::value;
+    uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SM_VAL);
+    uint32_t *hi32 = lo32 + T * T;
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
     unsigned src_mask = 0; // which of my CPT cells are sources
 #pragma unroll 4
@@ -188,9 +203,17 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             if (m_in == 0)
                 src_mask |= 1u << i;
         }
-        don[c] = (uint8_t)m_in;
-        reinterpret_cast<uint8_t *>(pend32)[c] = (uint8_t)m_in;
-        val[c] = v;
+        if constexpr (CNT) {
+            const unsigned long long u = (unsigned long long)v;
+            lo32[c] = ((unsigned)__popc(m_in) << 28) | (unsigned)(u & 0xFFFFFFu);
+            if (FINAL)
+                hi32[c] = (unsigned)(u >> 24);
+        }
+        else {
+            don[c] = (uint8_t)m_in;
+            reinterpret_cast<uint8_t *>(pend32)[c] = (uint8_t)m_in;
+            val[c] = v;
+        }
     }
     __syncthreads();
 
@@ -199,7 +222,11 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         if (!((src_mask >> i) & 1u))
             continue;
         int cur = tid + i * THREADS;
-        V v = val[cur];
+        V v;
+        if constexpr (CNT)
+            v = (V)(lo32[cur] & 0x0FFFFFFFu) + (FINAL ? ((V)hi32[cur] << 24) : (V)0);
+        else
+            v = val[cur];
         for (;;) {
             const int ly = cur / T, lx = cur - ly * T;
             const int link = eff[(ly + 1) * RP + lx + XO];
@@ -218,25 +245,42 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                 break;
             }
             const int rc = ny * T + nx;
-            const int kme = (1 - dr) * 3 + (1 - dc); // me, seen from the receiver
-            const unsigned bit = 1u << (kme < 4 ? kme : kme - 1);
-            const int sh = 8 * (rc & 3);
-            __threadfence_block();
-            const unsigned old = atomicAnd(&pend32[rc >> 2], ~(bit << sh));
-            if (((old >> sh) & 0xFFu) != bit)
-                break; // other donors still to come; the last one continues
-            __threadfence_block();
-            // gather in fixed neighbour order: own weight + all donors
-            V sum = val[rc];
-            unsigned m = don[rc];
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const int kk = b < 4 ? b : b + 1;
-                sum += val[rc + (kk / 3 - 1) * T + (kk % 3 - 1)];
+            if constexpr (CNT) {
+                // one atomic hands the value on and counts the arrival
+                const unsigned long long u = (unsigned long long)v;
+                const unsigned v_lo = (unsigned)(u & 0xFFFFFFu), v_hi = (unsigned)(u >> 24);
+                if (FINAL && v_hi) {
+                    atomicAdd(&hi32[rc], v_hi);
+                    __threadfence_block();
+                }
+                const unsigned old = atomicAdd(&lo32[rc], v_lo + 0xF0000000u);
+                if ((old >> 28) != 1u)
+                    break; // other donors still to come; the last one continues
+                v = (V)((old & 0x0FFFFFFFu) + v_lo);
+                if (FINAL)
+                    v += (V)hi32[rc] << 24;
             }
-            val[rc] = sum;
-            v = sum;
+            else {
+                const int kme = (1 - dr) * 3 + (1 - dc); // me, seen from the receiver
+                const unsigned bit = 1u << (kme < 4 ? kme : kme - 1);
+                const int sh = 8 * (rc & 3);
+                fence_acq_rel_cta();
+                const unsigned old = atomicAnd(&pend32[rc >> 2], ~(bit << sh));
+                if (((old >> sh) & 0xFFu) != bit)
+                    break;
+                fence_acq_rel_cta();
+                // gather in fixed neighbour order: own weight + all donors
+                V sum = val[rc];
+                unsigned m = don[rc];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int kk = b < 4 ? b : b + 1;
+                    sum += val[rc + (kk / 3 - 1) * T + (kk % 3 - 1)];
+                }
+                val[rc] = sum;
+                v = sum;
+            }
             cur = rc;
         }
     }
@@ -301,7 +345,12 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             const int yy = ly + 1, xx = lx + XO;
             const uint8_t b = pk[yy * RP + xx];
             const bool null = b & HT_DIR_NULL;
-            const double a = (double)val[c];
+            double a;
+            if constexpr (CNT)
+                a = (double)((unsigned long long)(lo32[c] & 0x0FFFFFFFu) +
+                             ((unsigned long long)hi32[c] << 24));
+            else
+                a = (double)val[c];
             if (p.acc)
                 p.acc[(y0 + ly) * p.acc_ld + x0 + lx] = null ? __longlong_as_double(0x7ff8000000000000LL) : a;
             if (p.dir_out) {
@@ -336,17 +385,342 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     }
 }
 
+// ===========================================================================
+// Count modes (cell counts, taint counts): lean integer kernels.
+//   stage A  acc_local_cnt_kernel : receiver offsets -> scatter in-degree ->
+//            flattened chain walk with ONE shared atomic per edge (the 32-bit
+//            word carries [donors to come : 4 | value : 28]); writes the
+//            tile-local count of every cell (<= 4096, u16) for stage C.
+//   stage C  acc_final_cnt_kernel : final = tile-local count + inflow of every
+//            entry cell upstream; each entry's inflow is added along its path to
+//            the tile exit by an independent walker (no ordering needed).
+// ===========================================================================
+constexpr int16_t R_TERM = 0;       // no receiver
+constexpr int16_t R_EXIT = 0x4000;  // receiver lies outside the tile
+constexpr int SMC_ROFF = SM_EFF;                  // int16[T*T]
+constexpr int SMC_LO = SMC_ROFF + T * T * 2;      // uint32[T*T]
+constexpr int SMC_BAR = SMC_LO + T * T * 4;
+constexpr int SMC_TOTAL = SMC_BAR + 16;
+
+struct RingBounds { int ry_lo, ry_hi, rx_lo, rx_hi; }; // usable ring-tile cells (inclusive)
+
+__device__ __forceinline__ RingBounds ring_bounds(const AccArgs &p, int64_t x0, int64_t y0)
+{
+    RingBounds b;
+    b.ry_lo = (int)max((int64_t)0, 1 - y0 - p.halo_top);
+    b.ry_hi = (int)min((int64_t)RH - 1, p.rows + p.halo_bot - y0);
+    b.rx_lo = (int)max((int64_t)XO - 1, XO - x0);
+    b.rx_hi = (int)min((int64_t)XO + T, XO + p.cols - 1 - x0);
+    return b;
+}
+
+__device__ __forceinline__ bool ring_valid(const uint8_t *pk, const RingBounds &rb, int yy, int xx)
+{
+    return yy >= rb.ry_lo && yy <= rb.ry_hi && xx >= rb.rx_lo && xx <= rb.rx_hi &&
+           !(pk[yy * RP + xx] & HT_DIR_NULL);
+}
+
+// perimeter slot k of a th x tw tile -> (ly, lx); false for duplicates / unused
+__device__ __forceinline__ bool perimeter_cell(int k, int th, int tw, int &ly, int &lx)
+{
+    if (k < T) { ly = 0; lx = k; }
+    else if (k < 2 * T) { ly = th - 1; lx = k - T; if (th == 1) return false; }
+    else if (k < 3 * T) { ly = k - 2 * T; lx = 0; if (ly == 0 || ly >= th - 1) return false; }
+    else { ly = k - 3 * T; lx = tw - 1; if (ly == 0 || ly >= th - 1 || tw == 1) return false; }
+    return ly < th && lx < tw;
+}
+
+template <int WMODE>
+__global__ void __launch_bounds__(THREADS, 7)
+acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *pk = smem_raw;
+    int16_t *roff = reinterpret_cast<int16_t *>(smem_raw + SMC_ROFF);
+    uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SMC_LO);
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMC_BAR);
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
+    if (tid == 0) {
+        ht::mbar_init(&bar, 1);
+        ht::fence_mbar_init();
+        ht::mbar_expect_tx(&bar, RH * RP);
+        ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
+    }
+    __syncthreads();
+    ht::mbar_wait(&bar, 0);
+
+    const RingBounds rb = ring_bounds(p, x0, y0);
+    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
+
+    // ---- S1: receiver offset and weight of every tile cell
+#pragma unroll 4
+    for (int i = 0; i < CPT; i++) {
+        const int c = tid + i * THREADS;
+        const int ly = c >> 6, lx = c & (T - 1);
+        const int yy = ly + 1, xx = lx + XO;
+        const uint8_t b = pk[yy * RP + xx];
+        const bool ok = ly < th && lx < tw && !(b & HT_DIR_NULL);
+        int16_t o = R_TERM;
+        unsigned w = 0;
+        if (ok) {
+            w = WMODE == W_ONE ? 1u : ((b & HT_DIR_TAINT) ? 1u : 0u);
+            const int code = b & HT_DIR_CODE;
+            if (!(b & (HT_DIR_NEG | HT_DIR_EDGE)) && code >= 1 && code <= 8) {
+                const int dr = code_dr(code), dc = code_dc(code);
+                if (ring_valid(pk, rb, yy + dr, xx + dc)) {
+                    const int ny = ly + dr, nx = lx + dc;
+                    o = (ny >= 0 && ny < th && nx >= 0 && nx < tw) ? (int16_t)(dr * T + dc) : R_EXIT;
+                }
+            }
+        }
+        roff[c] = o;
+        lo32[c] = w;
+    }
+    __syncthreads();
+
+    // ---- S2: in-degree by scatter (count field of the receiver's word)
+#pragma unroll 4
+    for (int i = 0; i < CPT; i++) {
+        const int c = tid + i * THREADS;
+        const int16_t o = roff[c];
+        if (o != R_TERM && o != R_EXIT)
+            atomicAdd(&lo32[c + o], 1u << 28);
+    }
+    __syncthreads();
+    unsigned src_mask = 0;
+#pragma unroll 4
+    for (int i = 0; i < CPT; i++)
+        src_mask |= ((lo32[tid + i * THREADS] >> 28) == 0u ? 1u : 0u) << i;
+    __syncthreads();
+
+    // ---- S3: topological propagation; a lane whose chain ends picks up its next
+    // source at once, so the lanes of a warp stay busy
+    {
+        bool active = false;
+        int cur = 0;
+        unsigned v = 0;
+        for (;;) {
+            if (!active) {
+                if (!src_mask)
+                    break;
+                const int i = __ffs(src_mask) - 1;
+                src_mask &= src_mask - 1;
+                cur = tid + i * THREADS;
+                v = lo32[cur] & 0x0FFFFFFFu;
+                active = true;
+            }
+            const int16_t o = roff[cur];
+            if (o == R_TERM) {
+                active = false;
+                continue;
+            }
+            if (o == R_EXIT) {
+                // flow leaves the tile: feed the boundary graph
+                const int code = pk[((cur >> 6) + 1) * RP + (cur & (T - 1)) + XO] & HT_DIR_CODE;
+                const int64_t lr = y0 + (cur >> 6) + code_dr(code), gc = x0 + (cur & (T - 1)) + code_dc(code);
+                const int64_t s = lr < 0 ? vslot_of(p, false, gc)
+                                : lr >= p.rows ? vslot_of(p, true, gc)
+                                               : slot_of(p, lr, gc);
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.base) + s, (unsigned long long)v);
+                active = false;
+                continue;
+            }
+            const int rc = cur + o;
+            const unsigned old = atomicAdd(&lo32[rc], v + 0xF0000000u);
+            if ((old >> 28) != 1u) {
+                active = false; // other donors still to come; the last one continues
+                continue;
+            }
+            v += old & 0x0FFFFFFFu;
+            cur = rc;
+        }
+    }
+    __syncthreads();
+
+    // ---- S4a: where does the path of each entry cell leave the tile?
+    for (int k = tid; k < SLOTS; k += THREADS) {
+        int ly, lx;
+        if (!perimeter_cell(k, th, tw, ly, lx))
+            continue;
+        const int yy = ly + 1, xx = lx + XO;
+        if (pk[yy * RP + xx] & HT_DIR_NULL)
+            continue;
+        bool entry = false;
+#pragma unroll
+        for (int kk = 0; kk < 9; kk++) {
+            if (kk == 4)
+                continue;
+            const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
+            const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
+            if (in_tile || !ring_valid(pk, rb, ny, nx))
+                continue;
+            const uint8_t u = pk[ny * RP + nx];
+            entry |= !(u & (HT_DIR_NEG | HT_DIR_EDGE)) && (u & HT_DIR_CODE) == win2code(8 - kk);
+        }
+        if (!entry)
+            continue;
+        int cur = ly * T + lx;
+        int16_t o;
+        while ((o = roff[cur]) != R_TERM && o != R_EXIT)
+            cur += o;
+        int32_t nxt = TERMINAL;
+        if (o == R_EXIT) {
+            const int code = pk[((cur >> 6) + 1) * RP + (cur & (T - 1)) + XO] & HT_DIR_CODE;
+            const int64_t lr = y0 + (cur >> 6) + code_dr(code), gc = x0 + (cur & (T - 1)) + code_dc(code);
+            nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
+                          : lr >= p.rows ? vslot_of(p, true, gc)
+                                         : slot_of(p, lr, gc));
+        }
+        p.next[slot_of(p, y0 + ly, x0 + lx)] = nxt;
+    }
+
+    // ---- S4b: tile-local counts for stage C
+#pragma unroll 4
+    for (int i = 0; i < CPT; i++) {
+        const int c = tid + i * THREADS;
+        const int ly = c >> 6, lx = c & (T - 1);
+        if (ly < th && lx < tw)
+            p.lacc[(y0 + ly) * p.lacc_ld + x0 + lx] = (uint16_t)lo32[c];
+    }
+}
+
+constexpr int SMF_LO = T * T;               // after the 64x64 packed tile
+constexpr int SMF_HI = SMF_LO + T * T * 4;
+constexpr int SMF_BAR = SMF_HI + T * T * 4;
+constexpr int SMF_TOTAL = SMF_BAR + 16;
+
+template <int WMODE>
+__global__ void __launch_bounds__(THREADS, 6)
+acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *pk = smem_raw; // 64 x 64, no ring
+    uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SMF_LO); // value = hi * 2^20 + lo
+    uint32_t *hi32 = reinterpret_cast<uint32_t *>(smem_raw + SMF_HI);
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMF_BAR);
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
+    if (tid == 0) {
+        ht::mbar_init(&bar, 1);
+        ht::fence_mbar_init();
+        ht::mbar_expect_tx(&bar, T * T);
+        ht::tma_load_2d(pk, &map, (int)x0, (int)y0 + p.halo_top, &bar);
+    }
+    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
+    // tile-local counts while the TMA is in flight
+#pragma unroll 4
+    for (int i = 0; i < CPT; i++) {
+        const int c = tid + i * THREADS;
+        const int ly = c >> 6, lx = c & (T - 1);
+        lo32[c] = (ly < th && lx < tw) ? p.lacc[(y0 + ly) * p.lacc_ld + x0 + lx] : 0u;
+        hi32[c] = 0u;
+    }
+    __syncthreads();
+    ht::mbar_wait(&bar, 0);
+
+    // ---- walkers: one per entry cell with inflow
+    for (int k = tid; k < SLOTS; k += THREADS) {
+        int ly, lx;
+        if (!perimeter_cell(k, th, tw, ly, lx))
+            continue;
+        const unsigned long long inflow =
+            reinterpret_cast<const unsigned long long *>(p.inflow)[slot_of(p, y0 + ly, x0 + lx)];
+        if (!inflow)
+            continue;
+        const unsigned i_lo = (unsigned)(inflow & 0xFFFFFu), i_hi = (unsigned)(inflow >> 20);
+        int cy = ly, cx = lx;
+        for (;;) {
+            const int cur = cy * T + cx;
+            if (i_lo)
+                atomicAdd(&lo32[cur], i_lo);
+            if (i_hi)
+                atomicAdd(&hi32[cur], i_hi);
+            const uint8_t b = pk[cur];
+            const int code = b & HT_DIR_CODE;
+            if ((b & (HT_DIR_NEG | HT_DIR_EDGE)) || code < 1 || code > 8)
+                break;
+            cy += code_dr(code);
+            cx += code_dc(code);
+            if (cy < 0 || cy >= th || cx < 0 || cx >= tw || (pk[cy * T + cx] & HT_DIR_NULL))
+                break;
+        }
+    }
+    __syncthreads();
+
+    // ---- outputs
+#pragma unroll 2
+    for (int i = 0; i < CPT; i++) {
+        const int c = tid + i * THREADS;
+        const int ly = c >> 6, lx = c & (T - 1);
+        if (ly >= th || lx >= tw)
+            continue;
+        const uint8_t b = pk[c];
+        const bool null = b & HT_DIR_NULL;
+        const unsigned long long cnt = ((unsigned long long)hi32[c] << 20) + lo32[c];
+        const double a = (double)cnt;
+        if (p.acc)
+            p.acc[(y0 + ly) * p.acc_ld + x0 + lx] = null ? __longlong_as_double(0x7ff8000000000000LL) : a;
+        if (WMODE == W_ONE && p.dir_out) {
+            const int code = b & HT_DIR_CODE;
+            int out;
+            if (null)
+                out = -128;
+            else if (b & HT_DIR_NEG)
+                out = -code;
+            else if ((b & HT_DIR_EDGE) && cnt >= 60ull) {
+                // rule R5: an edge cell that is a swale (|acc| >= 60) gets its outward
+                // code back: first neighbour outside the raster / NULL in the order
+                // S,N,W,E,NE,SW,SE,NW (rare: read the neighbours from global memory)
+                out = 0;
+#pragma unroll
+                for (int ct = 7; ct >= 0; ct--) {
+                    const int kk = ct2win(ct);
+                    const int64_t lr = y0 + ly + kk / 3 - 1, gc = x0 + lx + kk % 3 - 1;
+                    const int64_t gr = p.row0 + lr;
+                    bool outside = gr < 0 || gr >= p.total_rows || gc < 0 || gc >= p.cols;
+                    if (!outside)
+                        outside = p.packed[lr * p.packed_ld + gc] & HT_DIR_NULL;
+                    if (outside)
+                        out = -win2code(kk);
+                }
+                if (out == 0)
+                    out = code; // not an edge after all (foreign packed grid)
+            }
+            else
+                out = code;
+            p.dir_out[(y0 + ly) * p.dir_ld + x0 + lx] = (int8_t)out;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // stage B: boundary-graph resolve (subtree sums over a forest) by pointer doubling
 // ---------------------------------------------------------------------------
 template <typename V>
 __global__ void __launch_bounds__(256)
-coarse_resolve_kernel(V *aggA, V *aggB, int32_t *ptrA, int32_t *ptrB, int32_t *rootA,
-                      int32_t *rootB, int64_t n, int *flags, int *rounds_out)
+coarse_resolve_kernel(const V *base0, const int32_t *next0, V *aggA, V *aggB, int32_t *ptrA,
+                      int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n, int *flags,
+                      int *rounds_out)
 {
     cg::grid_group grid = cg::this_grid();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // the graph itself (base0 / next0) is left untouched so that it can be
+    // resolved again after inflow from other bands has been added
+    for (int64_t u = t0; u < n; u += stride) {
+        aggA[u] = base0[u];
+        ptrA[u] = next0[u];
+        if (rootA)
+            rootA[u] = (int32_t)u;
+    }
+    grid.sync();
     int round = 0;
     for (;; round++) {
         // agg_{k+1} starts as agg_k
@@ -393,17 +767,11 @@ coarse_resolve_kernel(V *aggA, V *aggB, int32_t *ptrA, int32_t *ptrB, int32_t *r
         *rounds_out = round + 1;
 }
 
-template <typename V>
-__global__ void init_root_kernel(int32_t *root, int64_t n)
-{
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n;
-         u += (int64_t)gridDim.x * blockDim.x)
-        root[u] = (int32_t)u;
-}
-
 struct Workspace {
-    void *aggA, *aggB;
-    int32_t *ptrA, *ptrB, *rootA, *rootB;
+    uint16_t *lacc;
+    int64_t lacc_ld;
+    void *base0, *aggA, *aggB;
+    int32_t *next0, *ptrA, *ptrB, *rootA, *rootB;
     int *flags;
     int64_t nslots;
 };
@@ -418,7 +786,9 @@ int64_t nslots_of(int64_t rows, int64_t cols)
 size_t workspace_bytes(int64_t rows, int64_t cols)
 {
     const int64_t n = nslots_of(rows, cols);
-    return 2 * align_up(n * 8) + 4 * align_up(n * 4) + align_up(64 * sizeof(int)) + 256;
+    const int64_t lacc_ld = (cols + 7) / 8 * 8;
+    return 3 * align_up(n * 8) + 5 * align_up(n * 4) + align_up(64 * sizeof(int)) +
+           align_up((size_t)rows * lacc_ld * 2) + 256;
 }
 
 int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
@@ -427,13 +797,17 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
         return HT_ERR_WORKSPACE;
     const int64_t n = nslots_of(rows, cols);
     uint8_t *b = (uint8_t *)(((uintptr_t)ws + 255) / 256 * 256);
+    w.base0 = b; b += align_up(n * 8);
     w.aggA = b; b += align_up(n * 8);
     w.aggB = b; b += align_up(n * 8);
+    w.next0 = (int32_t *)b; b += align_up(n * 4);
     w.ptrA = (int32_t *)b; b += align_up(n * 4);
     w.ptrB = (int32_t *)b; b += align_up(n * 4);
     w.rootA = (int32_t *)b; b += align_up(n * 4);
     w.rootB = (int32_t *)b; b += align_up(n * 4);
-    w.flags = (int *)b;
+    w.flags = (int *)b; b += align_up(64 * sizeof(int));
+    w.lacc = (uint16_t *)b;
+    w.lacc_ld = (cols + 7) / 8 * 8;
     w.nslots = n;
     return 0;
 }
@@ -450,8 +824,29 @@ template <typename V, int WMODE, bool FINAL>
 int launch_tile(const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
 {
     auto kern = acc_tile_kernel<V, WMODE, FINAL>;
-    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    kern<<<p.tiles_x * p.tiles_y, THREADS, SM_TOTAL, st>>>(map, p);
+    // counts keep 4 (stage A) or 8 (stage C) bytes per cell, fp64 sums the full layout
+    const int smem = std::is_same<V, double>::value ? SM_TOTAL
+                                                    : SM_VAL + T * T * (FINAL ? 8 : 4) + 16;
+    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<p.tiles_x * p.tiles_y, THREADS, smem, st>>>(map, p);
+    HT_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int WMODE, bool FINAL>
+int launch_cnt(const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
+{
+    const int ntiles = p.tiles_x * p.tiles_y;
+    if (FINAL) {
+        auto kern = acc_final_cnt_kernel<WMODE>;
+        HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMF_TOTAL));
+        kern<<<ntiles, THREADS, SMF_TOTAL, st>>>(map, p);
+    }
+    else {
+        auto kern = acc_local_cnt_kernel<WMODE>;
+        HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMC_TOTAL));
+        kern<<<ntiles, THREADS, SMC_TOTAL, st>>>(map, p);
+    }
     HT_LAUNCH_CHECK();
     return 0;
 }
@@ -460,15 +855,17 @@ template <bool FINAL>
 int dispatch_tile(int mode, const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
 {
     switch (mode) {
-    case W_ONE: return launch_tile<unsigned long long, W_ONE, FINAL>(map, p, st);
-    case W_TAINT: return launch_tile<unsigned long long, W_TAINT, FINAL>(map, p, st);
+    case W_ONE: return launch_cnt<W_ONE, FINAL>(map, p, st);
+    case W_TAINT: return launch_cnt<W_TAINT, FINAL>(map, p, st);
     case W_F32: return launch_tile<double, W_F32, FINAL>(map, p, st);
     }
     return HT_ERR_ARG;
 }
 
 template <typename V>
-int launch_resolve(Workspace &w, bool with_root, int *rounds_dev, cudaStream_t st)
+int launch_resolve(const void *base0, const int32_t *next0, void *aggA_, void *aggB_,
+                   int32_t *ptrA, int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n,
+                   int *flags, int *rounds_dev, cudaStream_t st)
 {
     auto kern = coarse_resolve_kernel<V>;
     int per_sm = 0;
@@ -479,18 +876,13 @@ int launch_resolve(Workspace &w, bool with_root, int *rounds_dev, cudaStream_t s
     HT_CUDA_TRY(cudaGetDevice(&dev));
     HT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = sms * (per_sm > 4 ? 4 : per_sm);
-    const int64_t need = (w.nslots + 255) / 256;
+    const int64_t need = (n + 255) / 256;
     if (grid > need)
         grid = (int)(need > 0 ? need : 1);
-    HT_CUDA_TRY(cudaMemsetAsync(w.flags, 0, 64 * sizeof(int), st));
-    V *aggA = (V *)w.aggA, *aggB = (V *)w.aggB;
-    int32_t *rootA = with_root ? w.rootA : nullptr, *rootB = with_root ? w.rootB : nullptr;
-    if (with_root) {
-        init_root_kernel<V><<<ht::kSMs * 4, 256, 0, st>>>(w.rootA, w.nslots);
-        HT_LAUNCH_CHECK();
-    }
-    int64_t n = w.nslots;
-    void *args[] = {&aggA, &aggB, &w.ptrA, &w.ptrB, &rootA, &rootB, &n, &w.flags, &rounds_dev};
+    HT_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+    const V *b0 = (const V *)base0;
+    V *aggA = (V *)aggA_, *aggB = (V *)aggB_;
+    void *args[] = {&b0, &next0, &aggA, &aggB, &ptrA, &ptrB, &rootA, &rootB, &n, &flags, &rounds_dev};
     HT_CUDA_TRY(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(256), args, 0, st));
     return 0;
 }
@@ -508,6 +900,7 @@ int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t tota
     p.base = nullptr; p.next = nullptr; p.inflow = nullptr;
     p.w = nullptr; p.w_ld = 0; p.has_wnd = 0; p.wnd = 0.f;
     p.acc = nullptr; p.acc_ld = 0; p.dir_out = nullptr; p.dir_ld = 0;
+    p.lacc = nullptr; p.lacc_ld = 0; p.packed = nullptr; p.packed_ld = 0;
     return 0;
 }
 
@@ -541,10 +934,12 @@ extern "C" int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t ro
     CUtensorMap map;
     if ((rc = make_packed_map(map, packed, packed_ld, rows, cols, p.halo_top, p.halo_bot)))
         return rc;
-    HT_CUDA_TRY(cudaMemsetAsync(wk.aggA, 0, wk.nslots * 8, st));
-    HT_CUDA_TRY(cudaMemsetAsync(wk.ptrA, 0xFF, wk.nslots * 4, st));
-    p.base = wk.aggA; p.next = wk.ptrA;
+    HT_CUDA_TRY(cudaMemsetAsync(wk.base0, 0, wk.nslots * 8, st));
+    HT_CUDA_TRY(cudaMemsetAsync(wk.next0, 0xFF, wk.nslots * 4, st));
+    p.base = wk.base0; p.next = wk.next0;
     p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
+    p.lacc = wk.lacc; p.lacc_ld = wk.lacc_ld;
+    p.packed = packed; p.packed_ld = packed_ld;
     return dispatch_tile<false>(mode, map, p, st);
 }
 
@@ -560,10 +955,63 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
     int rc = carve(ws, ws_bytes, rows, cols, wk);
     if (rc)
         return rc;
+    int32_t *rA = want_roots ? wk.rootA : nullptr, *rB = want_roots ? wk.rootB : nullptr;
     if (mode == W_F32)
-        return launch_resolve<double>(wk, want_roots != 0, rounds_dev, (cudaStream_t)stream);
-    return launch_resolve<unsigned long long>(wk, want_roots != 0, rounds_dev, (cudaStream_t)stream);
+        return launch_resolve<double>(wk.base0, wk.next0, wk.aggA, wk.aggB, wk.ptrA, wk.ptrB, rA,
+                                      rB, wk.nslots, wk.flags, rounds_dev, (cudaStream_t)stream);
+    return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.aggA, wk.aggB, wk.ptrA,
+                                              wk.ptrB, rA, rB, wk.nslots, wk.flags, rounds_dev,
+                                              (cudaStream_t)stream);
 }
+
+// Byte offsets (from the workspace pointer) of the boundary-graph arrays, for the
+// row-band host code: layout[0..8] = base0, aggA, aggB (= resolved inflow), next0,
+// ptrA, ptrB, rootA, rootB (= last node of each path), flags; layout[9] = number
+// of slots, layout[10] = first virtual slot (cells of the band above, then of the
+// band below, `cols` each).
+extern "C" int ht_acc_workspace_layout(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
+                                       int64_t *layout11)
+{
+    if (!layout11 || rows <= 0 || cols <= 0)
+        return HT_ERR_ARG;
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    if (rc)
+        return rc;
+    const uint8_t *b = (const uint8_t *)ws;
+    const void *ptrs[9] = {wk.base0, wk.aggA, wk.aggB, wk.next0, wk.ptrA, wk.ptrB, wk.rootA, wk.rootB, wk.flags};
+    for (int i = 0; i < 9; i++)
+        layout11[i] = (int64_t)((const uint8_t *)ptrs[i] - b);
+    layout11[9] = wk.nslots;
+    layout11[10] = wk.nslots - 2 * cols;
+    return HT_OK;
+}
+
+// Generic forest resolve (subtree sums): agg_out[v] = base[v] + sum of base[u] over
+// all u whose path along next[] passes through v.  Resolves the band-level boundary
+// graph of a row-band sharded raster.  is_f64: values are doubles, else u64.
+extern "C" int ht_forest_resolve(const void *base, const int32_t *next, int64_t n, int is_f64,
+                                 void *agg_out, void *tmp, size_t tmp_bytes, void *stream)
+{
+    if (n == 0)
+        return HT_OK;
+    if (!base || !next || !agg_out || !tmp || n < 0)
+        return HT_ERR_ARG;
+    const size_t need = align_up(n * 8) + 2 * align_up(n * 4) + 512 + 256;
+    if (tmp_bytes < need)
+        return HT_ERR_WORKSPACE;
+    uint8_t *b = (uint8_t *)(((uintptr_t)tmp + 255) / 256 * 256);
+    void *aggA = b; b += align_up(n * 8);
+    int32_t *ptrA = (int32_t *)b; b += align_up(n * 4);
+    int32_t *ptrB = (int32_t *)b; b += align_up(n * 4);
+    int *flags = (int *)b;
+    if (is_f64)
+        return launch_resolve<double>(base, next, aggA, agg_out, ptrA, ptrB, nullptr, nullptr, n,
+                                      flags, nullptr, (cudaStream_t)stream);
+    return launch_resolve<unsigned long long>(base, next, aggA, agg_out, ptrA, ptrB, nullptr, nullptr,
+                                              n, flags, nullptr, (cudaStream_t)stream);
+}
+
 
 // Stage C.
 extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows,
@@ -586,8 +1034,16 @@ extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t ro
     if ((rc = carve(ws, ws_bytes, rows, cols, wk)))
         return rc;
     CUtensorMap map;
-    if ((rc = make_packed_map(map, packed, packed_ld, rows, cols, p.halo_top, p.halo_bot)))
+    if (mode == W_F32)
+        rc = make_packed_map(map, packed, packed_ld, rows, cols, p.halo_top, p.halo_bot);
+    else
+        rc = ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1,
+                             packed - (int64_t)p.halo_top * packed_ld,
+                             rows + p.halo_top + p.halo_bot, cols, packed_ld, T, T, false);
+    if (rc)
         return rc;
+    p.lacc = wk.lacc; p.lacc_ld = wk.lacc_ld;
+    p.packed = packed; p.packed_ld = packed_ld;
     p.inflow = wk.aggB;
     p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
     p.acc = acc; p.acc_ld = acc_ld; p.dir_out = dir_out; p.dir_ld = dir_ld;

@@ -56,16 +56,52 @@ def upload(a: ArrayLike, dtype: torch.dtype, align_elems: int, device,
         t = torch.from_numpy(arr)
         if t.dtype != dtype:
             t = t.to(dtype)
-        view.copy_(t.pin_memory(), non_blocking=True)
+        if not t.is_pinned():
+            # pageable host memory: stage through a cached pinned buffer
+            stage = _pinned(t.shape, t.dtype, "upload")
+            stage.copy_(t)
+            t = stage
+        view.copy_(t, non_blocking=True)
     return buf, ld
 
 
-def download(view: torch.Tensor) -> np.ndarray:
-    """Device -> pinned host -> numpy (synchronises the current stream)."""
-    host = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
-    host.copy_(view, non_blocking=True)
+_PINNED = {}
+
+
+def _pinned(shape, dtype, tag: str) -> torch.Tensor:
+    """Reusable pinned staging buffer (cudaHostAlloc is far slower than the copy)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    key = (tag, dtype)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+        _PINNED[key] = buf
+    return buf[:n].view(*shape)
+
+
+def download(view: torch.Tensor, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Device -> host (synchronises the current stream).  With ``out`` (a C-contiguous
+    array of the right shape/dtype, ideally page-locked) the copy lands there
+    directly; otherwise it goes through a cached pinned buffer into a new array."""
+    if out is not None:
+        t = torch.from_numpy(out)
+        if tuple(t.shape) != tuple(view.shape) or t.dtype != view.dtype or not t.is_contiguous():
+            raise ValueError("`out` has the wrong shape, dtype or layout")
+        if t.is_pinned():
+            t.copy_(view, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
+        stage = _pinned(view.shape, view.dtype, "download")
+        stage.copy_(view, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        t.copy_(stage)
+        return out
+    stage = _pinned(view.shape, view.dtype, "download")
+    stage.copy_(view, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return host.numpy().copy()
+    return stage.numpy().copy()
 
 
 def nodata_args(nodata: Optional[float]) -> Tuple[int, float]:

@@ -56,6 +56,8 @@ SIGNATURES = {
                      _f32, _p, _i64, _p, _i64, _p, C.c_size_t, _p],
     "ht_acc_f64": [_p, _i64, _i64, _i64, _int, _p, _i64, _int, _f32, _p, _i64, _p, _i64,
                    _p, C.c_size_t, _p],
+    "ht_acc_workspace_layout": [_i64, _i64, _p, C.c_size_t, C.POINTER(C.c_int64)],
+    "ht_forest_resolve": [_p, _p, _i64, _int, _p, _p, C.c_size_t, _p],
     "ht_acc_apply_sign": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p],
     "ht_synth_dem_f32": [_p, _i64, _i64, _i64, _u64, _i64, _i64, _int, _f32, _p],
     "ht_synth_weight_f32": [_p, _i64, _i64, _i64, _u64, _i64, _p],

@@ -1,0 +1,354 @@
+"""Row-band sharding of the hot path across the GPUs of one box
+(BASELINE.json north_star: "The DEM is row-band sharded
+... Stencil halos and accumulation boundary flows are exchanged with NCCL over
+NVLink, and the boundary graph is resolved iteratively until no flow changes").
+
+One process per GPU (torchrun); ``torch.distributed`` is the plumbing:
+  * DEM halo rows (2 per shared side for D8, 1 for the terrain stencils) travel
+    with point-to-point send/recv between band neighbours;
+  * accumulation: every band resolves its own tile boundary graph first, then
+    publishes two small tables per shared side -- the flow it delivers into each
+    cell of the neighbour's edge row, and, for each of its own edge-row cells,
+    through which edge cell the path that enters there leaves the band again.
+    The tables (2 x cols x 12 B per band) are all-gathered, every rank resolves
+    the band-level forest (same pointer-doubling kernel, <= 2*P*cols nodes), adds
+    the inflow it receives to its own boundary graph and resolves that once
+    more.  Exact in one exchange; no per-iteration collective.
+
+``BandEngine`` holds the orchestration and is backend-agnostic so that the
+exchange logic is testable on CPU (gloo, world_size 2) with a CPU stand-in for
+the kernels; ``CudaBand`` is the product backend.
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+T = 64          # tile edge of the accumulation kernels (csrc/ht_acc.cu)
+SLOTS = 4 * T
+
+
+def band_edge_slots(rows: int, cols: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Boundary-graph slot of every cell of the band's first / last row
+    (mirrors slot_of() in csrc/ht_acc.cu)."""
+    tiles_x = (cols + T - 1) // T
+    c = torch.arange(cols, device=device, dtype=torch.int64)
+    tx, lx = c // T, c % T
+    top = tx * SLOTS + lx
+    ty = (rows - 1) // T
+    h = rows - ty * T
+    bot = (ty * tiles_x + tx) * SLOTS + (lx if h == 1 else T + lx)
+    return top, bot
+
+
+def build_band_graph(delivered: torch.Tensor, link: torch.Tensor):
+    """Band-level forest from the all-gathered tables.
+
+    delivered[b, s, c]: flow band b hands to the cell in column c of the edge row
+    of the band above (s = 0) / below (s = 1).  link[b, s, c]: for band b's own
+    cell in column c of its first (s = 0) / last (s = 1) row, -1 if a path that
+    enters there ends inside the band, else side*cols + c' of the foreign cell it
+    reaches (side 0 = band above).  Node (b, s, c) = that own cell; returns
+    (base, next) flattened.
+    """
+    P, _, cols = delivered.shape
+    base = torch.zeros_like(delivered)
+    base[1:, 0] = delivered[:-1, 1]   # my first row receives what the band above sends down
+    base[:-1, 1] = delivered[1:, 0]   # my last row receives what the band below sends up
+    b = torch.arange(P, device=link.device, dtype=torch.int64).view(P, 1, 1)
+    L = link.to(torch.int64)
+    side = torch.div(L, cols, rounding_mode="floor")
+    c2 = L - side * cols
+    up = ((b - 1) * 2 + 1) * cols + c2    # last row of the band above
+    down = ((b + 1) * 2 + 0) * cols + c2  # first row of the band below
+    nxt = torch.where(L < 0, torch.full_like(L, -1), torch.where(side == 0, up, down))
+    return base.reshape(-1), nxt.reshape(-1).to(torch.int32)
+
+
+class BandEngine:
+    """Runs flow_direction_accumulation / terrain on one row band per rank."""
+
+    def __init__(self, rank: int, world: int, rows: int, cols: int, total_rows: int,
+                 csx: float, csy: float, nodata: Optional[float] = None, band=None,
+                 group=None, row0: Optional[int] = None):
+        self.rank, self.world = rank, world
+        self.rows, self.cols, self.total_rows = rows, cols, total_rows
+        self.group = group
+        self.launches = 0
+        if band is None:
+            if row0 is None:
+                row0 = rank * rows if world > 1 else 0
+            band = CudaBand(rows, cols, row0, total_rows, csx, csy, nodata,
+                            has_above=rank > 0, has_below=rank < world - 1)
+        self.band = band
+
+    # ----------------------------------------------------------------- data
+    def generate_synthetic(self, seed: int, with_nulls: bool = False):
+        """Own rows only; halos arrive by exchange like for any other DEM."""
+        self.band.generate_synthetic(seed, with_nulls)
+
+    def load(self, dem):
+        self.band.load(dem)
+
+    def dem_view(self):
+        return self.band.dem_view()
+
+    def validate(self):
+        if self.world > 1:
+            self.exchange_halos(2)
+        c = self.band.validate()
+        if self.world > 1:
+            dist.all_reduce(c, group=self.group)
+        c = c.cpu()
+        return int(c[0]), int(c[1])
+
+    # ----------------------------------------------------------------- comm
+    def exchange_halos(self, depth: int):
+        """`depth` DEM rows to / from each band neighbour (send/recv pairs)."""
+        band, ops, recvs = self.band, [], []
+        if self.rank > 0:
+            send = band.edge_rows(top=True, depth=depth)
+            recv = torch.empty_like(send)
+            ops += [dist.P2POp(dist.isend, send, self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, recv, self.rank - 1, self.group)]
+            recvs.append((True, recv))
+        if self.rank < self.world - 1:
+            send = band.edge_rows(top=False, depth=depth)
+            recv = torch.empty_like(send)
+            ops += [dist.P2POp(dist.isend, send, self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, recv, self.rank + 1, self.group)]
+            recvs.append((False, recv))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        for top, recv in recvs:
+            band.set_halo_rows(top=top, rows=recv)
+
+    # ----------------------------------------------------------------- hot path
+    def flow_direction_accumulation(self, mode: int = 0):
+        band = self.band
+        if self.world > 1:
+            self.exchange_halos(2)
+        band.direction()
+        self.accumulate(mode)
+
+    def accumulate(self, mode: int = 0):
+        band = self.band
+        band.local(mode)
+        if self.world == 1:
+            band.resolve(False)
+            band.final(mode)
+            self.launches += band.take_launches()
+            return
+        band.resolve(True)
+        delivered, link = band.band_tables(mode)
+        P = self.world
+        all_d = torch.empty((P,) + tuple(delivered.shape), dtype=delivered.dtype,
+                            device=delivered.device)
+        all_l = torch.empty((P,) + tuple(link.shape), dtype=link.dtype, device=link.device)
+        dist.all_gather_into_tensor(all_d, delivered.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_l, link.contiguous(), group=self.group)
+        base, nxt = build_band_graph(all_d, all_l)
+        inflow = band.forest_resolve(base, nxt, mode).view(P, 2, self.cols)
+        band.add_inflow(inflow[self.rank, 0], inflow[self.rank, 1], mode)
+        band.resolve(False)
+        band.final(mode)
+        self.launches += band.take_launches()
+
+    def terrain(self, scale: float = 1.0, percent: bool = False):
+        if self.world > 1:
+            self.exchange_halos(1)
+        out = self.band.terrain(scale, percent)
+        self.launches += self.band.take_launches()
+        return out
+
+    def results(self):
+        return self.band.results()
+
+    def time_kernels(self, iters: int = 5):
+        return self.band.time_kernels(iters)
+
+
+class CudaBand:
+    """One rank's row band in HBM and the sm_100a kernels on it (product backend)."""
+
+    def __init__(self, rows, cols, row0, total_rows, csx, csy, nodata, has_above, has_below):
+        from . import _native as N, _device as D
+        self.N, self.D = N, D
+        self.dev = D.require_cuda()
+        if (has_above or has_below) and rows < 2:
+            raise ValueError("row bands need at least 2 rows")
+        self.rows, self.cols, self.row0, self.total_rows = rows, cols, row0, total_rows
+        self.csx, self.csy, self.nodata = float(abs(csx)), float(abs(csy)), nodata
+        self.htop, self.hbot = (2 if has_above else 0), (2 if has_below else 0)
+        self.dem, self.ld = D.empty_padded(rows, cols, torch.float32, self.dev, 4, 2, 2)
+        self.packed, self.pld = D.empty_padded(rows, cols, torch.uint8, self.dev, 16, 1, 1)
+        self.acc, self.ald = D.empty_padded(rows, cols, torch.float64, self.dev, 2)
+        self.dir, self.dld = D.empty_padded(rows, cols, torch.int8, self.dev, 16)
+        self.ws = torch.empty(int(N.lib.ht_acc_workspace_bytes(rows, cols)), dtype=torch.uint8,
+                              device=self.dev)
+        import ctypes
+        lay = (ctypes.c_int64 * 11)()
+        N.check(N.lib.ht_acc_workspace_layout(rows, cols, self.ws.data_ptr(), self.ws.numel(), lay),
+                "ht_acc_workspace_layout")
+        self.lay = list(lay)
+        self.nslots, self.vfirst = self.lay[9], self.lay[10]
+        self.idx_top, self.idx_bot = band_edge_slots(rows, cols, self.dev)
+        self.weight, self.wld, self.wnd = None, 0, None
+        self._launches = 0
+        self._tmp = None
+
+    # ---- pointers
+    def _dem0(self):
+        return self.dem.data_ptr() + 2 * self.ld * 4
+
+    def _packed0(self):
+        return self.packed.data_ptr() + self.pld
+
+    def _ws_view(self, k, dtype):
+        off, n = self.lay[k], self.nslots
+        size = n * (8 if dtype in (torch.int64, torch.float64) else 4)
+        return self.ws[off:off + size].view(dtype)
+
+    def _vdtype(self, mode):
+        return torch.float64 if mode == self.N.MODE_WEIGHTED else torch.int64
+
+    def take_launches(self):
+        n, self._launches = self._launches, 0
+        return n
+
+    # ---- data
+    def generate_synthetic(self, seed, with_nulls=False):
+        nd = -32767.0 if self.nodata is None else self.nodata
+        self.N.call("ht_synth_dem_f32", self._dem0(), self.rows, self.cols, self.ld, seed,
+                    self.row0, self.total_rows, int(with_nulls), float(nd), self.D.stream_ptr())
+
+    def load(self, dem):
+        a = self.D.as_2d(dem)
+        view = self.dem[2:2 + self.rows, :self.cols]
+        if isinstance(a, torch.Tensor):
+            view.copy_(a.to(torch.float32), non_blocking=True)
+        else:
+            import numpy as np
+            view.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)),
+                       non_blocking=False)
+
+    def set_weight(self, w, nodata=None):
+        self.weight, self.wld = self.D.upload(w, torch.float32, 4, self.dev)
+        self.wnd = nodata
+
+    def dem_view(self):
+        return self.dem[2:2 + self.rows, :self.cols]
+
+    def edge_rows(self, top, depth):
+        r0 = 2 if top else 2 + self.rows - depth
+        return self.dem[r0:r0 + depth, :self.cols].contiguous()
+
+    def set_halo_rows(self, top, rows):
+        depth = rows.shape[0]
+        r0 = 2 - depth if top else 2 + self.rows
+        self.dem[r0:r0 + depth, :self.cols].copy_(rows)
+
+    # ---- kernels
+    def validate(self):
+        counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        has, nd = self.D.nodata_args(self.nodata)
+        self.N.call("ht_d8_validate_conditioned_f32", self._dem0(), self.rows, self.cols, self.ld,
+                    has, nd, self.row0, self.total_rows, self.htop, self.hbot, counts.data_ptr(),
+                    self.D.stream_ptr())
+        return counts
+
+    def direction(self):
+        has, nd = self.D.nodata_args(self.nodata)
+        self.N.call("ht_d8_f32", self._dem0(), self.rows, self.cols, self.ld, has, nd, self.csx,
+                    self.csy, self.row0, self.total_rows, self.htop, self.hbot, self._packed0(),
+                    self.pld, self.D.stream_ptr())
+        self._launches += 1
+
+    def _wargs(self, mode):
+        if mode == self.N.MODE_WEIGHTED:
+            has, nd = self.D.nodata_args(self.wnd)
+            return self.weight.data_ptr(), self.wld, has, nd
+        return None, 0, 0, 0.0
+
+    def local(self, mode=0):
+        w, wld, has, nd = self._wargs(mode)
+        self.N.call("ht_acc_local", self._packed0(), self.pld, self.rows, self.cols, self.row0,
+                    self.total_rows, int(self.htop > 0), int(self.hbot > 0), mode, w, wld, has, nd,
+                    self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
+        self._launches += 1
+        self._mode = mode
+
+    def resolve(self, want_roots):
+        self.N.call("ht_acc_resolve", self.rows, self.cols, self._mode, int(want_roots),
+                    self.ws.data_ptr(), self.ws.numel(), None, self.D.stream_ptr())
+        self._launches += 1
+
+    def final(self, mode=0, want_dir=True):
+        w, wld, has, nd = self._wargs(mode)
+        self.N.call("ht_acc_final", self._packed0(), self.pld, self.rows, self.cols, self.row0,
+                    self.total_rows, int(self.htop > 0), int(self.hbot > 0), mode, w, wld, has, nd,
+                    self.acc.data_ptr(), self.ald,
+                    self.dir.data_ptr() if (want_dir and mode == 0) else None, self.dld,
+                    self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
+        self._launches += 1
+
+    def band_tables(self, mode=0):
+        """(delivered [2, cols], link [2, cols]) after resolve(want_roots=True)."""
+        vd = self._vdtype(mode)
+        inflow = self._ws_view(2, vd)       # aggB
+        root = self._ws_view(7, torch.int32)  # rootB
+        delivered = inflow[self.vfirst:self.vfirst + 2 * self.cols].view(2, self.cols).clone()
+        link = torch.stack([root[self.idx_top], root[self.idx_bot]]).to(torch.int64) - self.vfirst
+        link = torch.where(link >= 0, link, torch.full_like(link, -1)).to(torch.int32)
+        return delivered, link
+
+    def forest_resolve(self, base, nxt, mode=0):
+        n = base.numel()
+        out = torch.empty_like(base)
+        need = 16 * n + 4096
+        if self._tmp is None or self._tmp.numel() < need:
+            self._tmp = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        self.N.call("ht_forest_resolve", base.data_ptr(), nxt.data_ptr(), n,
+                    int(mode == self.N.MODE_WEIGHTED), out.data_ptr(), self._tmp.data_ptr(),
+                    self._tmp.numel(), self.D.stream_ptr())
+        self._launches += 1
+        return out
+
+    def add_inflow(self, top, bot, mode=0):
+        base0 = self._ws_view(0, self._vdtype(mode))
+        base0.index_add_(0, self.idx_top, top)
+        base0.index_add_(0, self.idx_bot, bot)
+
+    def terrain(self, scale=1.0, percent=False):
+        outs = [self.D.empty_padded(self.rows, self.cols, torch.float32, self.dev, 4) for _ in range(3)]
+        has, nd = self.D.nodata_args(self.nodata)
+        self.N.call("ht_terrain_fused_f32", self._dem0(), self.rows, self.cols, self.ld, has, nd,
+                    self.csx, self.csy, float(scale), int(percent), outs[0][0].data_ptr(),
+                    outs[1][0].data_ptr(), outs[2][0].data_ptr(), outs[0][1],
+                    int(self.htop > 0), int(self.hbot > 0), self.D.stream_ptr())
+        self._launches += 2
+        return tuple(o[0][:, :self.cols] for o in outs)
+
+    def results(self):
+        return self.dir[:, :self.cols], self.acc[:, :self.cols]
+
+    def time_kernels(self, iters=5):
+        """Average device time of each stage (CUDA events on the launching stream)."""
+        stages = [("d8_kernel", self.direction),
+                  ("acc_tile_kernel<local>", lambda: self.local(0)),
+                  ("coarse_resolve_kernel", lambda: self.resolve(False)),
+                  ("acc_tile_kernel<final>", lambda: self.final(0))]
+        out = []
+        for name, fn in stages:
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out.append({"name": name, "ms": e0.elapsed_time(e1) / iters})
+        self.take_launches()
+        return out

@@ -79,14 +79,18 @@ def accumulate(packed: torch.Tensor, pld: int, rows: int, cols: int, mode: int,
 
 def flow_direction_accumulation_arrays(dem: D.ArrayLike, nodata: Optional[float] = None,
                                        csx: float = 1.0, csy: float = 1.0,
-                                       positive_only: bool = True, validate: bool = True):
+                                       positive_only: bool = True, validate: bool = True,
+                                       out_direction: Optional[np.ndarray] = None,
+                                       out_accumulation: Optional[np.ndarray] = None):
     """Array-level ``flow_direction_accumulation``.
 
     Returns ``(direction int8, accumulation float64)``: GRASS codes 1..8 (1 = NE,
     counter-clockwise), negative = flows off the region / into NULL, -128 where
     the DEM is NULL; accumulation = upslope cell count incl. the cell, NaN where
     NULL, negative "likely underestimates" unless ``positive_only``.
-    numpy in -> numpy out; CUDA tensor in -> CUDA tensors out.
+    numpy in -> numpy out; CUDA tensor in -> CUDA tensors out.  ``out_direction``
+    / ``out_accumulation`` (host arrays, ideally page-locked) receive the results
+    without an intermediate copy.
     """
     dev = D.require_cuda()
     on_host = not isinstance(dem, torch.Tensor)
@@ -111,7 +115,7 @@ def flow_direction_accumulation_arrays(dem: D.ArrayLike, nodata: Optional[float]
                packed.data_ptr(), pld, rows, cols, D.stream_ptr())
     dview, aview = dout[:, :cols], acc[:, :cols]
     if on_host:
-        return D.download(dview), D.download(aview)
+        return D.download(dview, out_direction), D.download(aview, out_accumulation)
     return dview, aview
 
 

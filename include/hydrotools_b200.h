@@ -103,6 +103,18 @@ int ht_dir_unpack_i8(const uint8_t *packed, int64_t packed_ld, int64_t rows,
  * dir_out != NULL, the final GRASS direction codes (int8, -128 = NULL).
  * ht_acc_f64 = A + B + C for an unsharded raster. */
 size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols);
+/* byte offsets of the boundary-graph arrays inside the workspace (row-band host
+ * code reads the band tables from them): layout11[0..8] = base0, aggA,
+ * aggB (resolved inflow), next0, ptrA, ptrB, rootA, rootB (last node of each
+ * slot's path), flags; [9] = slots; [10] = first virtual slot (cells of the band
+ * above, then of the band below, `cols` each). */
+int ht_acc_workspace_layout(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
+                            int64_t *layout11_host);
+/* subtree sums over a forest given by next[] (< 0 = root); the band-level
+ * boundary graph of a row-band sharded raster is resolved with it.
+ * tmp_bytes >= 16*n + 2048. */
+int ht_forest_resolve(const void *base, const int32_t *next, int64_t n, int is_f64,
+                      void *agg_out, void *tmp, size_t tmp_bytes, void *stream);
 int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
                  int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
                  int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
