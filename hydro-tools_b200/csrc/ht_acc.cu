@@ -67,6 +67,8 @@ struct AccArgs {
     int64_t acc_ld;
     int8_t *dir_out;
     int64_t dir_ld;
+    int32_t *list;            // slots that are boundary-graph nodes (stage A out)
+    int *nlist;               // their number (device counter)
     uint16_t *lacc;           // tile-local counts, stage A -> stage C (count modes)
     int64_t lacc_ld;
     const uint8_t *packed;    // owned row 0 of the packed grid (rare global look-ups)
@@ -103,6 +105,37 @@ __device__ __forceinline__ int64_t vslot_of(const AccArgs &p, bool bottom, int64
 }
 
 __device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+// perimeter slot k of a th x tw tile -> (ly, lx); false for duplicates / unused
+__device__ __forceinline__ bool perimeter_cell(int k, int th, int tw, int &ly, int &lx)
+{
+    if (k < T) { ly = 0; lx = k; }
+    else if (k < 2 * T) { ly = th - 1; lx = k - T; if (th == 1) return false; }
+    else if (k < 3 * T) { ly = k - 2 * T; lx = 0; if (ly == 0 || ly >= th - 1) return false; }
+    else { ly = k - 3 * T; lx = tw - 1; if (ly == 0 || ly >= th - 1 || tw == 1) return false; }
+    return ly < th && lx < tw;
+}
+
+static_assert(SLOTS == THREADS, "one perimeter slot per thread");
+
+// Every thread of the CTA calls this once (convergent).  Entry cells record their
+// successor and are appended to the list of boundary-graph nodes, one global
+// atomic per warp.
+__device__ __forceinline__ void publish_entry(const AccArgs &p, bool entry, int64_t slot, int32_t nxt)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, entry);
+    if (!m)
+        return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader)
+        base = atomicAdd(p.nlist, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (entry) {
+        p.list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)slot;
+        p.next[slot] = nxt;
+    }
+}
 
 template <typename V> __device__ __forceinline__ void atomic_add_v(V *p, V v);
 template <> __device__ __forceinline__ void atomic_add_v<unsigned long long>(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
@@ -288,52 +321,43 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 
     if (!FINAL) {
         // ---- S4a: where does the path of each entry cell leave the tile?
-        // perimeter cell index k -> (ly, lx)
-        for (int k = tid; k < SLOTS; k += THREADS) {
+        {
+            const int k = tid; // one perimeter slot per thread
             int ly, lx;
-            if (k < T) { ly = 0; lx = k; }
-            else if (k < 2 * T) { ly = th - 1; lx = k - T; }
-            else if (k < 3 * T) { ly = k - 2 * T; lx = 0; }
-            else { ly = k - 3 * T; lx = tw - 1; }
-            if (ly >= th || lx >= tw)
-                continue;
-            // each perimeter cell has exactly one slot: skip duplicates of corners
-            // and of 1-cell-thick tiles
-            if (k >= T && k < 2 * T && th == 1) continue;
-            if (k >= 2 * T && (ly == 0 || ly == th - 1)) continue;
-            if (k >= 3 * T && tw == 1) continue;
-            const int yy = ly + 1, xx = lx + XO;
-            if (!valid(yy, xx))
-                continue;
             bool entry = false;
-#pragma unroll
-            for (int kk = 0; kk < 9; kk++) {
-                if (kk == 4)
-                    continue;
-                const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
-                const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
-                entry |= !in_tile && eff[ny * RP + nx] == win2code(8 - kk);
-            }
-            if (!entry)
-                continue;
             int32_t nxt = TERMINAL;
-            int cy = ly, cx = lx;
-            for (;;) {
-                const int link = eff[(cy + 1) * RP + cx + XO];
-                if (!link)
-                    break;
-                const int ny = cy + code_dr(link), nx = cx + code_dc(link);
-                if (ny < 0 || ny >= th || nx < 0 || nx >= tw) {
-                    const int64_t lr = y0 + ny, gc = x0 + nx;
-                    nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
-                                  : lr >= p.rows ? vslot_of(p, true, gc)
-                                                 : slot_of(p, lr, gc));
-                    break;
+            int64_t slot = 0;
+            if (perimeter_cell(k, th, tw, ly, lx) && valid(ly + 1, lx + XO)) {
+                const int yy = ly + 1, xx = lx + XO;
+#pragma unroll
+                for (int kk = 0; kk < 9; kk++) {
+                    if (kk == 4)
+                        continue;
+                    const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
+                    const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
+                    entry |= !in_tile && eff[ny * RP + nx] == win2code(8 - kk);
                 }
-                cy = ny;
-                cx = nx;
+                if (entry) {
+                    slot = slot_of(p, y0 + ly, x0 + lx);
+                    int cy = ly, cx = lx;
+                    for (;;) {
+                        const int link = eff[(cy + 1) * RP + cx + XO];
+                        if (!link)
+                            break;
+                        const int ny = cy + code_dr(link), nx = cx + code_dc(link);
+                        if (ny < 0 || ny >= th || nx < 0 || nx >= tw) {
+                            const int64_t lr = y0 + ny, gc = x0 + nx;
+                            nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
+                                          : lr >= p.rows ? vslot_of(p, true, gc)
+                                                         : slot_of(p, lr, gc));
+                            break;
+                        }
+                        cy = ny;
+                        cx = nx;
+                    }
+                }
             }
-            p.next[slot_of(p, y0 + ly, x0 + lx)] = nxt;
+            publish_entry(p, entry, slot, nxt);
         }
     }
     else {
@@ -397,10 +421,12 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // ===========================================================================
 constexpr int16_t R_TERM = 0;       // no receiver
 constexpr int16_t R_EXIT = 0x4000;  // receiver lies outside the tile
+constexpr int16_t R_NULL = 0x4001;  // NULL cell / outside the raster
 constexpr int SMC_ROFF = SM_EFF;                  // int16[T*T]
 constexpr int SMC_LO = SMC_ROFF + T * T * 2;      // uint32[T*T]
-constexpr int SMC_BAR = SMC_LO + T * T * 4;
-constexpr int SMC_TOTAL = SMC_BAR + 16;
+constexpr int SMC_Q = SMC_LO + T * T * 4;         // uint16[T*T] queue of source cells
+constexpr int SMC_BAR = SMC_Q + T * T * 2;        // mbarrier, then queue head / size
+constexpr int SMC_TOTAL = SMC_BAR + 32;
 
 struct RingBounds { int ry_lo, ry_hi, rx_lo, rx_hi; }; // usable ring-tile cells (inclusive)
 
@@ -420,31 +446,25 @@ __device__ __forceinline__ bool ring_valid(const uint8_t *pk, const RingBounds &
            !(pk[yy * RP + xx] & HT_DIR_NULL);
 }
 
-// perimeter slot k of a th x tw tile -> (ly, lx); false for duplicates / unused
-__device__ __forceinline__ bool perimeter_cell(int k, int th, int tw, int &ly, int &lx)
-{
-    if (k < T) { ly = 0; lx = k; }
-    else if (k < 2 * T) { ly = th - 1; lx = k - T; if (th == 1) return false; }
-    else if (k < 3 * T) { ly = k - 2 * T; lx = 0; if (ly == 0 || ly >= th - 1) return false; }
-    else { ly = k - 3 * T; lx = tw - 1; if (ly == 0 || ly >= th - 1 || tw == 1) return false; }
-    return ly < th && lx < tw;
-}
-
 template <int WMODE>
-__global__ void __launch_bounds__(THREADS, 7)
+__global__ void __launch_bounds__(THREADS, 5)
 acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *pk = smem_raw;
     int16_t *roff = reinterpret_cast<int16_t *>(smem_raw + SMC_ROFF);
     uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SMC_LO);
+    uint16_t *queue = reinterpret_cast<uint16_t *>(smem_raw + SMC_Q);
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMC_BAR);
+    int *qctl = reinterpret_cast<int *>(smem_raw + SMC_BAR + 8); // [0] head, [1] size
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
     if (tid == 0) {
+        qctl[0] = 0;
+        qctl[1] = 0;
         ht::mbar_init(&bar, 1);
         ht::fence_mbar_init();
         ht::mbar_expect_tx(&bar, RH * RP);
@@ -464,7 +484,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         const int yy = ly + 1, xx = lx + XO;
         const uint8_t b = pk[yy * RP + xx];
         const bool ok = ly < th && lx < tw && !(b & HT_DIR_NULL);
-        int16_t o = R_TERM;
+        int16_t o = ok ? R_TERM : R_NULL;
         unsigned w = 0;
         if (ok) {
             w = WMODE == W_ONE ? 1u : ((b & HT_DIR_TAINT) ? 1u : 0u);
@@ -487,35 +507,45 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     for (int i = 0; i < CPT; i++) {
         const int c = tid + i * THREADS;
         const int16_t o = roff[c];
-        if (o != R_TERM && o != R_EXIT)
+        if (o != R_TERM && o < R_EXIT)
             atomicAdd(&lo32[c + o], 1u << 28);
     }
     __syncthreads();
-    unsigned src_mask = 0;
+    // sources (no donor inside the tile) go to a queue shared by the whole CTA
+    {
+        unsigned src_mask = 0;
 #pragma unroll 4
-    for (int i = 0; i < CPT; i++)
-        src_mask |= ((lo32[tid + i * THREADS] >> 28) == 0u ? 1u : 0u) << i;
+        for (int i = 0; i < CPT; i++) {
+            const int c = tid + i * THREADS;
+            src_mask |= ((lo32[c] >> 28) == 0u && roff[c] != R_NULL ? 1u : 0u) << i;
+        }
+        int pos = src_mask ? atomicAdd(&qctl[1], __popc(src_mask)) : 0;
+        while (src_mask) {
+            const int i = __ffs(src_mask) - 1;
+            src_mask &= src_mask - 1;
+            queue[pos++] = (uint16_t)(tid + i * THREADS);
+        }
+    }
     __syncthreads();
 
-    // ---- S3: topological propagation; a lane whose chain ends picks up its next
-    // source at once, so the lanes of a warp stay busy
+    // ---- S3: topological propagation.  A lane follows a chain for as long as it is
+    // the last donor to arrive, then takes the next source from the queue, so the
+    // lanes of a warp stay busy until only the longest trunks are left.
     {
-        bool active = false;
-        int cur = 0;
+        const int qn = qctl[1];
+        int cur = -1;
         unsigned v = 0;
         for (;;) {
-            if (!active) {
-                if (!src_mask)
+            if (cur < 0) {
+                const int qi = atomicAdd(&qctl[0], 1);
+                if (qi >= qn)
                     break;
-                const int i = __ffs(src_mask) - 1;
-                src_mask &= src_mask - 1;
-                cur = tid + i * THREADS;
+                cur = queue[qi];
                 v = lo32[cur] & 0x0FFFFFFFu;
-                active = true;
             }
             const int16_t o = roff[cur];
             if (o == R_TERM) {
-                active = false;
+                cur = -1;
                 continue;
             }
             if (o == R_EXIT) {
@@ -526,13 +556,13 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                                 : lr >= p.rows ? vslot_of(p, true, gc)
                                                : slot_of(p, lr, gc);
                 atomicAdd(reinterpret_cast<unsigned long long *>(p.base) + s, (unsigned long long)v);
-                active = false;
+                cur = -1;
                 continue;
             }
             const int rc = cur + o;
             const unsigned old = atomicAdd(&lo32[rc], v + 0xF0000000u);
             if ((old >> 28) != 1u) {
-                active = false; // other donors still to come; the last one continues
+                cur = -1; // other donors still to come; the last one continues
                 continue;
             }
             v += old & 0x0FFFFFFFu;
@@ -542,40 +572,41 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     __syncthreads();
 
     // ---- S4a: where does the path of each entry cell leave the tile?
-    for (int k = tid; k < SLOTS; k += THREADS) {
+    {
+        const int k = tid; // one perimeter slot per thread
         int ly, lx;
-        if (!perimeter_cell(k, th, tw, ly, lx))
-            continue;
-        const int yy = ly + 1, xx = lx + XO;
-        if (pk[yy * RP + xx] & HT_DIR_NULL)
-            continue;
         bool entry = false;
-#pragma unroll
-        for (int kk = 0; kk < 9; kk++) {
-            if (kk == 4)
-                continue;
-            const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
-            const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
-            if (in_tile || !ring_valid(pk, rb, ny, nx))
-                continue;
-            const uint8_t u = pk[ny * RP + nx];
-            entry |= !(u & (HT_DIR_NEG | HT_DIR_EDGE)) && (u & HT_DIR_CODE) == win2code(8 - kk);
-        }
-        if (!entry)
-            continue;
-        int cur = ly * T + lx;
-        int16_t o;
-        while ((o = roff[cur]) != R_TERM && o != R_EXIT)
-            cur += o;
         int32_t nxt = TERMINAL;
-        if (o == R_EXIT) {
-            const int code = pk[((cur >> 6) + 1) * RP + (cur & (T - 1)) + XO] & HT_DIR_CODE;
-            const int64_t lr = y0 + (cur >> 6) + code_dr(code), gc = x0 + (cur & (T - 1)) + code_dc(code);
-            nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
-                          : lr >= p.rows ? vslot_of(p, true, gc)
-                                         : slot_of(p, lr, gc));
+        int64_t slot = 0;
+        if (perimeter_cell(k, th, tw, ly, lx) && !(pk[(ly + 1) * RP + lx + XO] & HT_DIR_NULL)) {
+            const int yy = ly + 1, xx = lx + XO;
+#pragma unroll
+            for (int kk = 0; kk < 9; kk++) {
+                if (kk == 4)
+                    continue;
+                const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
+                const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
+                if (in_tile || !ring_valid(pk, rb, ny, nx))
+                    continue;
+                const uint8_t u = pk[ny * RP + nx];
+                entry |= !(u & (HT_DIR_NEG | HT_DIR_EDGE)) && (u & HT_DIR_CODE) == win2code(8 - kk);
+            }
+            if (entry) {
+                slot = slot_of(p, y0 + ly, x0 + lx);
+                int cur = ly * T + lx;
+                int16_t o;
+                while ((o = roff[cur]) != R_TERM && o < R_EXIT)
+                    cur += o;
+                if (o == R_EXIT) {
+                    const int code = pk[((cur >> 6) + 1) * RP + (cur & (T - 1)) + XO] & HT_DIR_CODE;
+                    const int64_t lr = y0 + (cur >> 6) + code_dr(code), gc = x0 + (cur & (T - 1)) + code_dc(code);
+                    nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
+                                  : lr >= p.rows ? vslot_of(p, true, gc)
+                                                 : slot_of(p, lr, gc));
+                }
+            }
         }
-        p.next[slot_of(p, y0 + ly, x0 + lx)] = nxt;
+        publish_entry(p, entry, slot, nxt);
     }
 
     // ---- S4b: tile-local counts for stage C
@@ -706,15 +737,21 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 template <typename V>
 __global__ void __launch_bounds__(256)
 coarse_resolve_kernel(const V *base0, const int32_t *next0, V *aggA, V *aggB, int32_t *ptrA,
-                      int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n, int *flags,
-                      int *rounds_out)
+                      int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n,
+                      const int32_t *list, const int *nlist, int *flags, int *rounds_out)
 {
     cg::grid_group grid = cg::this_grid();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // only the slots in `list` are nodes (all n slots if there is no list)
+    const int64_t na = list ? (int64_t)*nlist : n;
     // the graph itself (base0 / next0) is left untouched so that it can be
     // resolved again after inflow from other bands has been added
-    for (int64_t u = t0; u < n; u += stride) {
+    if (rootA)
+        for (int64_t u = t0; u < n; u += stride)
+            rootB[u] = (int32_t)u; // slots that are not nodes end at themselves
+    for (int64_t i = t0; i < na; i += stride) {
+        const int64_t u = list ? list[i] : i;
         aggA[u] = base0[u];
         ptrA[u] = next0[u];
         if (rootA)
@@ -724,11 +761,14 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, V *aggA, V *aggB, in
     int round = 0;
     for (;; round++) {
         // agg_{k+1} starts as agg_k
-        for (int64_t u = t0; u < n; u += stride)
+        for (int64_t i = t0; i < na; i += stride) {
+            const int64_t u = list ? list[i] : i;
             aggB[u] = aggA[u];
+        }
         grid.sync();
         bool any = false;
-        for (int64_t u = t0; u < n; u += stride) {
+        for (int64_t i = t0; i < na; i += stride) {
+            const int64_t u = list ? list[i] : i;
             const int32_t q = ptrA[u];
             if (q >= 0) {
                 const V a = aggA[u];
@@ -757,7 +797,8 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, V *aggA, V *aggB, in
     // round + 1 rounds were run; an odd count leaves the result in the caller's "B"
     // buffers already, an even count leaves it in "A"
     if (round & 1) {
-        for (int64_t u = t0; u < n; u += stride) {
+        for (int64_t i = t0; i < na; i += stride) {
+            const int64_t u = list ? list[i] : i;
             aggB[u] = aggA[u];
             if (rootA)
                 rootB[u] = rootA[u];
@@ -767,12 +808,22 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, V *aggA, V *aggB, in
         *rounds_out = round + 1;
 }
 
+__global__ void append_range_kernel(int32_t *list, int *nlist, int32_t first, int32_t count)
+{
+    __shared__ int base;
+    if (threadIdx.x == 0)
+        base = atomicAdd(nlist, count);
+    __syncthreads();
+    for (int i = threadIdx.x; i < count; i += blockDim.x)
+        list[base + i] = first + i;
+}
+
 struct Workspace {
     uint16_t *lacc;
     int64_t lacc_ld;
     void *base0, *aggA, *aggB;
-    int32_t *next0, *ptrA, *ptrB, *rootA, *rootB;
-    int *flags;
+    int32_t *next0, *ptrA, *ptrB, *rootA, *rootB, *list;
+    int *flags, *nlist;
     int64_t nslots;
 };
 
@@ -787,7 +838,7 @@ size_t workspace_bytes(int64_t rows, int64_t cols)
 {
     const int64_t n = nslots_of(rows, cols);
     const int64_t lacc_ld = (cols + 7) / 8 * 8;
-    return 3 * align_up(n * 8) + 5 * align_up(n * 4) + align_up(64 * sizeof(int)) +
+    return 3 * align_up(n * 8) + 6 * align_up(n * 4) + align_up(128 * sizeof(int)) +
            align_up((size_t)rows * lacc_ld * 2) + 256;
 }
 
@@ -805,7 +856,9 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
     w.ptrB = (int32_t *)b; b += align_up(n * 4);
     w.rootA = (int32_t *)b; b += align_up(n * 4);
     w.rootB = (int32_t *)b; b += align_up(n * 4);
-    w.flags = (int *)b; b += align_up(64 * sizeof(int));
+    w.list = (int32_t *)b; b += align_up(n * 4);
+    w.flags = (int *)b; b += align_up(128 * sizeof(int));
+    w.nlist = w.flags + 64;
     w.lacc = (uint16_t *)b;
     w.lacc_ld = (cols + 7) / 8 * 8;
     w.nslots = n;
@@ -865,7 +918,8 @@ int dispatch_tile(int mode, const CUtensorMap &map, const AccArgs &p, cudaStream
 template <typename V>
 int launch_resolve(const void *base0, const int32_t *next0, void *aggA_, void *aggB_,
                    int32_t *ptrA, int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n,
-                   int *flags, int *rounds_dev, cudaStream_t st)
+                   const int32_t *list, const int *nlist, int *flags, int *rounds_dev,
+                   cudaStream_t st)
 {
     auto kern = coarse_resolve_kernel<V>;
     int per_sm = 0;
@@ -882,7 +936,7 @@ int launch_resolve(const void *base0, const int32_t *next0, void *aggA_, void *a
     HT_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
     const V *b0 = (const V *)base0;
     V *aggA = (V *)aggA_, *aggB = (V *)aggB_;
-    void *args[] = {&b0, &next0, &aggA, &aggB, &ptrA, &ptrB, &rootA, &rootB, &n, &flags, &rounds_dev};
+    void *args[] = {&b0, &next0, &aggA, &aggB, &ptrA, &ptrB, &rootA, &rootB, &n, &list, &nlist, &flags, &rounds_dev};
     HT_CUDA_TRY(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(256), args, 0, st));
     return 0;
 }
@@ -901,6 +955,7 @@ int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t tota
     p.w = nullptr; p.w_ld = 0; p.has_wnd = 0; p.wnd = 0.f;
     p.acc = nullptr; p.acc_ld = 0; p.dir_out = nullptr; p.dir_ld = 0;
     p.lacc = nullptr; p.lacc_ld = 0; p.packed = nullptr; p.packed_ld = 0;
+    p.list = nullptr; p.nlist = nullptr;
     return 0;
 }
 
@@ -940,7 +995,16 @@ extern "C" int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t ro
     p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
     p.lacc = wk.lacc; p.lacc_ld = wk.lacc_ld;
     p.packed = packed; p.packed_ld = packed_ld;
-    return dispatch_tile<false>(mode, map, p, st);
+    p.list = wk.list; p.nlist = wk.nlist;
+    HT_CUDA_TRY(cudaMemsetAsync(wk.nlist, 0, sizeof(int), st));
+    if ((rc = dispatch_tile<false>(mode, map, p, st)))
+        return rc;
+    if (p.halo_top || p.halo_bot) { // cells of the neighbouring bands are nodes too
+        append_range_kernel<<<1, 256, 0, st>>>(wk.list, wk.nlist, (int32_t)(wk.nslots - 2 * cols),
+                                               (int32_t)(2 * cols));
+        HT_LAUNCH_CHECK();
+    }
+    return HT_OK;
 }
 
 // Stage B.  Resolved inflow per slot ends up in the workspace ("aggB"); with
@@ -956,12 +1020,14 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
     if (rc)
         return rc;
     int32_t *rA = want_roots ? wk.rootA : nullptr, *rB = want_roots ? wk.rootB : nullptr;
+    HT_CUDA_TRY(cudaMemsetAsync(wk.aggB, 0, wk.nslots * 8, (cudaStream_t)stream));
     if (mode == W_F32)
         return launch_resolve<double>(wk.base0, wk.next0, wk.aggA, wk.aggB, wk.ptrA, wk.ptrB, rA,
-                                      rB, wk.nslots, wk.flags, rounds_dev, (cudaStream_t)stream);
+                                      rB, wk.nslots, wk.list, wk.nlist, wk.flags, rounds_dev,
+                                      (cudaStream_t)stream);
     return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.aggA, wk.aggB, wk.ptrA,
-                                              wk.ptrB, rA, rB, wk.nslots, wk.flags, rounds_dev,
-                                              (cudaStream_t)stream);
+                                              wk.ptrB, rA, rB, wk.nslots, wk.list, wk.nlist,
+                                              wk.flags, rounds_dev, (cudaStream_t)stream);
 }
 
 // Byte offsets (from the workspace pointer) of the boundary-graph arrays, for the
@@ -1007,9 +1073,9 @@ extern "C" int ht_forest_resolve(const void *base, const int32_t *next, int64_t 
     int *flags = (int *)b;
     if (is_f64)
         return launch_resolve<double>(base, next, aggA, agg_out, ptrA, ptrB, nullptr, nullptr, n,
-                                      flags, nullptr, (cudaStream_t)stream);
+                                      nullptr, nullptr, flags, nullptr, (cudaStream_t)stream);
     return launch_resolve<unsigned long long>(base, next, aggA, agg_out, ptrA, ptrB, nullptr, nullptr,
-                                              n, flags, nullptr, (cudaStream_t)stream);
+                                              n, nullptr, nullptr, flags, nullptr, (cudaStream_t)stream);
 }
 
 

@@ -33,8 +33,11 @@ constexpr int THREADS = 256;
 constexpr uint32_t STAGE_BYTES = BW * BH * 4;
 constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
 constexpr int DW = TW + 2, DH = TH + 2; // cells whose direction is computed
-constexpr int DP = 136;                 // pitch of the direction byte tile
-constexpr int32_t INVALID = INT32_MIN;  // NULL or outside the region
+constexpr int DX0 = 15;                 // dirs column of ring column 0: tile column 0 sits at 16
+constexpr int DP = 160;                 // pitch of the direction byte tile
+constexpr int32_t INVALID = 1 << 30;    // NULL or outside the region; valid |alt| < 2^29
+constexpr int32_t ALT_LIMIT = 1 << 29;
+constexpr int32_t DCLAMP = 1 << 27;     // differences are compared after clamping to +-2^27
 
 struct D8Args {
     int64_t rows, cols;       // owned rows, columns
@@ -47,12 +50,14 @@ struct D8Args {
     float inv_ew, inv_ns, inv_diag;
     uint8_t *packed;
     int64_t packed_ld;
-    unsigned long long *counters; // [0] pits, [1] ties (validation only)
+    unsigned long long *counters; // [0] pits, [1] ties, [2] elevations out of range
 };
 
-// window index (row-major 3x3) of r.watershed's neighbour order S,N,W,E,NE,SW,SE,NW
-// = {7, 1, 3, 5, 2, 6, 8, 0}, as a nibble table so it folds after unrolling
+// r.watershed's neighbour order ct = 0..7: S,N,W,E,NE,SW,SE,NW (cardinals first)
+// window cell (3x3 row-major) of neighbour ct = {7, 1, 3, 5, 2, 6, 8, 0}
 __device__ __forceinline__ int ct2win(int ct) { return (0x08625317u >> (4 * ct)) & 0xF; }
+// GRASS direction code of neighbour ct = {6, 2, 4, 8, 1, 5, 7, 3}
+__device__ __forceinline__ int ct2code(int ct) { return (0x37518426u >> (4 * ct)) & 0xF; }
 // GRASS direction code that points at window cell k = {3, 2, 1, 4, 0, 8, 5, 6, 7}
 __device__ __forceinline__ int win2code(int k) { return (int)((0x765804123ULL >> (4 * k)) & 0xF); }
 
@@ -76,32 +81,29 @@ __device__ __forceinline__ bool slope_less(int32_t a, double da, float inv_da, i
     return (double)a / da < (double)b / db;
 }
 
-// Packed direction byte of one cell from its 3x3 integer window.
+// Packed direction byte of one cell from its 3x3 integer window w0..w8.
+// Neighbours are ranked through keys (clamped difference << 3 | ct): one integer
+// min finds the lowest neighbour and which one it is; equal elevations (not a
+// conditioned DEM) fall to the earlier neighbour in r.watershed's order.
 template <bool VALIDATE>
-__device__ __forceinline__ uint8_t d8_cell(const int32_t w[9], int64_t gr, int64_t gc,
+__device__ __forceinline__ uint8_t d8_cell(int32_t w0, int32_t w1, int32_t w2, int32_t w3,
+                                           int32_t c, int32_t w5, int32_t w6, int32_t w7,
+                                           int32_t w8, bool border, int border_code,
                                            const D8Args &p, unsigned &pits, unsigned &ties)
 {
-    const int32_t c = w[4];
     if (c == INVALID)
         return HT_DIR_NULL;
-    const bool border = (gr == 0 || gc == 0 || gr == p.total_rows - 1 || gc == p.cols - 1);
-    bool any_invalid = false;
-    int32_t low = c;
-    int low_k = -1;
-#pragma unroll
-    for (int ct = 0; ct < 8; ct++) {
-        const int k = ct2win(ct);
-        const int32_t a = w[k];
-        if (a == INVALID) {
-            any_invalid = true;
-            continue;
-        }
-        if (a < low) {
-            low = a;
-            low_k = k;
-        }
-    }
+    auto key = [&](int32_t a, int ct) -> int32_t {
+        const int32_t d = max(min(a - c, DCLAMP - 1), -DCLAMP);
+        return (d << 3) | ct;
+    };
+    int32_t k0 = key(w7, 0), k1 = key(w1, 1), k2 = key(w3, 2), k3 = key(w5, 3);
+    int32_t k4 = key(w2, 4), k5 = key(w6, 5), k6 = key(w8, 6), k7 = key(w0, 7);
+    int32_t kmin = min(min(min(k0, k1), min(k2, k3)), min(min(k4, k5), min(k6, k7)));
+    const int32_t nmax = max(max(max(w0, w1), max(w2, w3)), max(max(w5, w6), max(w7, w8)));
+    const bool any_invalid = nmax == INVALID;
     if (VALIDATE) {
+        const int32_t w[9] = {w0, w1, w2, w3, c, w5, w6, w7, w8};
         bool tie = false;
 #pragma unroll
         for (int i = 0; i < 9; i++)
@@ -109,74 +111,65 @@ __device__ __forceinline__ uint8_t d8_cell(const int32_t w[9], int64_t gr, int64
             for (int j = i + 1; j < 9; j++)
                 tie |= (w[i] != INVALID && w[i] == w[j]);
         ties += tie;
-        pits += (!border && !any_invalid && low_k < 0);
+        pits += (!border && !any_invalid && kmin >= 0);
     }
     if (border || any_invalid) {
         // rule R2 + the re-pointing half of rule R4
-        if (low_k >= 0)
-            return (uint8_t)(win2code(low_k) | HT_DIR_EDGE);
-        int code;
-        if (border)
-            code = gr == 0 ? 2 : gc == 0 ? 4 : gr == p.total_rows - 1 ? 6 : 8;
-        else {
-            code = 0;
-#pragma unroll
-            for (int ct = 7; ct >= 0; ct--)
-                if (w[ct2win(ct)] == INVALID)
-                    code = win2code(ct2win(ct));
+        if (kmin < 0)
+            return (uint8_t)(ct2code(kmin & 7) | HT_DIR_EDGE);
+        int code = border_code;
+        if (!border) {
+            // first NULL neighbour in the order S,N,W,E,NE,SW,SE,NW
+            code = w0 == INVALID ? 3 : 0;
+            code = w8 == INVALID ? 7 : code;
+            code = w6 == INVALID ? 5 : code;
+            code = w2 == INVALID ? 1 : code;
+            code = w5 == INVALID ? 8 : code;
+            code = w3 == INVALID ? 4 : code;
+            code = w1 == INVALID ? 2 : code;
+            code = w7 == INVALID ? 6 : code;
         }
         return (uint8_t)(code | HT_DIR_EDGE | HT_DIR_NEG);
     }
-    if (low_k < 0)
-        return 0; // pit: not a conditioned DEM (ht_d8_validate_conditioned reports it)
-    // rule R4, local form.  lowest lower cardinal neighbour (N,W,E,S = 1,3,5,7)
-    int32_t card = c;
-    int card_k = -1;
-#pragma unroll
-    for (int k = 1; k < 9; k += 2)
-        if (w[k] < card) {
-            card = w[k];
-            card_k = k;
-        }
-    // diagonals below `card`, ascending; first one that is not skipped wins
-    unsigned done = 0;
-    for (int it = 0; it < 4; it++) {
-        int32_t dmin = card;
-        int dk = -1;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int k = q < 2 ? 2 * q : 2 * q + 2; // 0, 2, 6, 8
-            if (!((done >> q) & 1u) && w[k] < dmin) {
-                dmin = w[k];
-                dk = k;
-            }
-        }
-        if (dk < 0)
-            break;
-        // flanking cardinals of the diagonal, seen from the centre: same row
-        // (an ew_res step from the centre) and same column (an ns_res step)
-        const int32_t a_ew = (dk % 3 == 0) ? w[3] : w[5]; // (row 1, column of dk)
-        const int32_t a_ns = dk < 3 ? w[1] : w[7];        // (row of dk, column 1)
-        const int32_t rise = c - dmin;
+    // rule R4, local form: lower neighbours in ascending order; a cardinal is taken
+    // at once, a diagonal unless a flanking cardinal between it and the centre
+    // gives a steeper slope
+    for (int it = 0; it < 5; it++) {
+        if (kmin >= 0)
+            return 0; // pit: not a conditioned DEM (ht_d8_validate_conditioned reports it)
+        const int ct = kmin & 7;
+        if (ct < 4)
+            return (uint8_t)ct2code(ct);
+        // diagonal ct: 4 NE, 5 SW, 6 SE, 7 NW; flanks in the centre's row / column
+        const int32_t a_d = ct == 4 ? w2 : ct == 5 ? w6 : ct == 6 ? w8 : w0;
+        const int32_t a_ew = (ct == 4 || ct == 6) ? w5 : w3;
+        const int32_t a_ns = (ct == 4 || ct == 7) ? w1 : w7;
+        const int32_t rise = c - a_d;
         bool skip = false;
-        if (a_ew > dmin && a_ew < c)
+        if (a_ew > a_d && a_ew < c)
             skip = slope_less(rise, p.diag, p.inv_diag, c - a_ew, p.ew, p.inv_ew);
-        if (!skip && a_ns > dmin && a_ns < c)
+        if (!skip && a_ns > a_d && a_ns < c)
             skip = slope_less(rise, p.diag, p.inv_diag, c - a_ns, p.ns, p.inv_ns);
         if (!skip)
-            return (uint8_t)win2code(dk);
-        done |= 1u << (dk == 0 ? 0 : dk == 2 ? 1 : dk == 6 ? 2 : 3);
+            return (uint8_t)ct2code(ct);
+        // drop this diagonal and look at the next lowest neighbour
+        k4 = ct == 4 ? INT32_MAX : k4;
+        k5 = ct == 5 ? INT32_MAX : k5;
+        k6 = ct == 6 ? INT32_MAX : k6;
+        k7 = ct == 7 ? INT32_MAX : k7;
+        kmin = min(min(min(k0, k1), min(k2, k3)), min(min(k4, k5), min(k6, k7)));
     }
-    return (uint8_t)win2code(card_k);
+    return 0;
 }
 
 template <bool VALIDATE>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 3)
 d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[STAGES];
     __shared__ __align__(16) uint8_t dirs[DH * DP];
+    __shared__ int any_edge;
 
     const int tid = threadIdx.x;
     const int ntiles = p.tiles_x * p.tiles_y;
@@ -201,54 +194,73 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
                 issue(t, s);
         }
 
-    unsigned pits = 0, ties = 0;
+    unsigned pits = 0, ties = 0, range = 0;
     int k = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
         const int s = k % STAGES;
         int32_t *alt = reinterpret_cast<int32_t *>(smem_raw + (size_t)s * STAGE_STRIDE);
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int64_t x0 = (int64_t)tx * TW, y0 = (int64_t)ty * TH;
+        // rows / columns of the staged box that hold data of this raster
+        // (box row yy <-> owned row y0 - 2 + yy, box column xx <-> column x0 - PADL + xx)
+        const int ay_lo = (int)max((int64_t)0, 2 - y0 - p.halo_top);
+        const int ay_hi = (int)min((int64_t)BH - 1, p.rows + p.halo_bot - 1 - y0 + 2);
+        const int ax_lo = (int)max((int64_t)0, PADL - x0);
+        const int ax_hi = (int)min((int64_t)BW - 1, p.cols - 1 - x0 + PADL);
+        if (tid == 0)
+            any_edge = 0;
         ht::mbar_wait(&full[s], (k / STAGES) & 1);
 
         // ---- pass 0: float metres -> GRASS integer millimetres, in place
         for (int i = tid; i < BW * BH; i += THREADS) {
             const int yy = i / BW, xx = i - yy * BW;
-            const int64_t lr = y0 - 2 + yy, gc = x0 - PADL + xx; // owned-row index
-            const int64_t gr = p.row0 + lr;
             const float z = __int_as_float(alt[i]);
-            const bool inside = gc >= 0 && gc < p.cols && gr >= 0 && gr < p.total_rows &&
-                                lr >= -(int64_t)p.halo_top && lr < p.rows + p.halo_bot;
+            const bool inside = yy >= ay_lo && yy <= ay_hi && xx >= ax_lo && xx <= ax_hi;
             const bool null = !inside || (p.has_nodata && z == p.nodata) || z != z;
-            alt[i] = null ? INVALID : alt_from_f32(z);
+            int32_t a = INVALID;
+            if (!null) {
+                a = alt_from_f32(z);
+                if (a >= ALT_LIMIT || a <= -ALT_LIMIT) {
+                    a = a > 0 ? ALT_LIMIT - 1 : -ALT_LIMIT + 1;
+                    range++;
+                }
+            }
+            alt[i] = a;
         }
         __syncthreads();
 
         // ---- pass 1: direction byte of the tile and a 1-cell ring around it
+        bool edge_seen = false;
         for (int i = tid; i < DW * DH; i += THREADS) {
-            const int yy = i / DW, xx = i - yy * DW; // dirs coords; alt coords +1,+PADL-1
+            const int yy = i / DW, xx = i - yy * DW; // ring coords; box coords +1, +PADL-1
             const int32_t *a = alt + (yy + 1) * BW + (xx + PADL - 1);
-            int32_t w[9];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    w[r * 3 + c] = a[(r - 1) * BW + (c - 1)];
-            const int64_t lr = y0 - 1 + yy, gc = x0 - 1 + xx;
-            // only cells of the tile itself are counted by the validation
-            const bool own = yy >= 1 && yy <= TH && xx >= 1 && xx <= TW && lr < p.rows &&
-                             gc < p.cols;
+            const int64_t gr = p.row0 + y0 - 1 + yy, gc = x0 - 1 + xx;
+            const bool border = gr == 0 || gc == 0 || gr == p.total_rows - 1 || gc == p.cols - 1;
+            const int border_code = gr == 0 ? 2 : gc == 0 ? 4 : gr == p.total_rows - 1 ? 6 : 8;
             unsigned pp = 0, tt = 0;
-            dirs[yy * DP + xx] = d8_cell<VALIDATE>(w, p.row0 + lr, gc, p, pp, tt);
-            if (VALIDATE && own) {
-                pits += pp;
-                ties += tt;
+            const uint8_t b = d8_cell<VALIDATE>(a[-BW - 1], a[-BW], a[-BW + 1], a[-1], a[0], a[1],
+                                                a[BW - 1], a[BW], a[BW + 1], border, border_code,
+                                                p, pp, tt);
+            dirs[yy * DP + xx + DX0] = b;
+            edge_seen |= (b & HT_DIR_EDGE) != 0;
+            if (VALIDATE) {
+                // only cells of the tile itself are counted
+                const bool own = yy >= 1 && yy <= TH && xx >= 1 && xx <= TW &&
+                                 y0 - 1 + yy < p.rows && gc < p.cols;
+                if (own) {
+                    pits += pp;
+                    ties += tt;
+                }
             }
         }
+        if (edge_seen)
+            any_edge = 1;
         __syncthreads();
 
         // ---- pass 2: taint flag (rule R4: the cell an unworked seed is re-pointed
         // at has its accumulation sign flipped) and 128-bit row stores
         if (!VALIDATE) {
+            const bool need_taint = any_edge != 0;
             // item -> 16 consecutive cells of one row (8 items per row).  Rows -1 and
             // `rows` (first halo row of a neighbouring band) are stored too, without
             // the taint flag, for the accumulation stages' ring.
@@ -260,34 +272,39 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
                 const int64_t gc = x0 + seg * 16;
                 if (!(own || halo_row) || gc >= p.cols)
                     continue;
-                uint32_t out[4] = {0, 0, 0, 0};
+                const uint8_t *row = dirs + yy * DP + DX0 + 1 + seg * 16; // 16-B aligned
+                uint4 v = *reinterpret_cast<const uint4 *>(row);
+                if (need_taint && own) {
+                    uint32_t out[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int xx = 1 + seg * 16 + j;
-                    uint8_t b = dirs[yy * DP + xx];
-                    if (own && !(b & HT_DIR_NULL)) {
+                    for (int j = 0; j < 16; j++) {
+                        const uint8_t b = row[j];
+                        if (b & HT_DIR_NULL)
+                            continue;
                         bool taint = false;
 #pragma unroll
                         for (int kk = 0; kk < 9; kk++) {
                             if (kk == 4)
                                 continue;
-                            const uint8_t u = dirs[(yy + kk / 3 - 1) * DP + (xx + kk % 3 - 1)];
+                            const uint8_t u = row[j + (kk / 3 - 1) * DP + (kk % 3 - 1)];
                             // neighbour at window cell kk points back at me with code
                             // win2code(8 - kk)
                             taint |= ((u & (HT_DIR_EDGE | HT_DIR_NEG | HT_DIR_NULL)) == HT_DIR_EDGE) &&
                                      ((u & HT_DIR_CODE) == win2code(8 - kk));
                         }
                         if (taint)
-                            b |= HT_DIR_TAINT;
+                            out[j >> 2] |= (uint32_t)HT_DIR_TAINT << (8 * (j & 3));
                     }
-                    out[j >> 2] |= (uint32_t)b << (8 * (j & 3));
+                    v = make_uint4(out[0], out[1], out[2], out[3]);
                 }
                 uint8_t *dst = p.packed + lr * p.packed_ld + gc;
                 if (gc + 16 <= p.cols)
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
-                else
+                    *reinterpret_cast<uint4 *>(dst) = v;
+                else {
+                    const uint32_t out[4] = {v.x, v.y, v.z, v.w};
                     for (int j = 0; j < 16 && gc + j < p.cols; j++)
                         dst[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
+                }
             }
         }
 
@@ -304,6 +321,8 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             atomicAdd(&p.counters[0], (unsigned long long)pits);
         if (ties)
             atomicAdd(&p.counters[1], (unsigned long long)ties);
+        if (range)
+            atomicAdd(&p.counters[2], (unsigned long long)range);
     }
 }
 
@@ -341,7 +360,7 @@ int launch(const CUtensorMap &map, const D8Args &p, cudaStream_t st)
     const size_t smem = (size_t)STAGES * STAGE_STRIDE;
     HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = p.tiles_x * p.tiles_y;
-    int grid = 2 * ht::kSMs;
+    int grid = 3 * ht::kSMs;
     if (grid > ntiles)
         grid = ntiles;
     kern<<<grid, THREADS, smem, st>>>(map, p);
@@ -375,13 +394,13 @@ extern "C" int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t l
 extern "C" int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,
                                               int64_t ld, int has_nodata, float nodata,
                                               int64_t row0, int64_t total_rows, int halo_top,
-                                              int halo_bot, unsigned long long *counts2,
+                                              int halo_bot, unsigned long long *counts3,
                                               void *stream)
 {
-    if (!counts2)
+    if (!counts3)
         return HT_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    HT_CUDA_TRY(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), st));
+    HT_CUDA_TRY(cudaMemsetAsync(counts3, 0, 3 * sizeof(unsigned long long), st));
     if (rows == 0 || cols == 0)
         return HT_OK;
     D8Args p;
@@ -390,6 +409,6 @@ extern "C" int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, in
                    halo_top, halo_bot, p, map);
     if (rc)
         return rc;
-    p.counters = counts2;
+    p.counters = counts3;
     return launch<true>(map, p, st);
 }

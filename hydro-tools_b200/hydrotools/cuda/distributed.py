@@ -251,7 +251,7 @@ class CudaBand:
 
     # ---- kernels
     def validate(self):
-        counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        counts = torch.zeros(3, dtype=torch.int64, device=self.dev)
         has, nd = self.D.nodata_args(self.nodata)
         self.N.call("ht_d8_validate_conditioned_f32", self._dem0(), self.rows, self.cols, self.ld,
                     has, nd, self.row0, self.total_rows, self.htop, self.hbot, counts.data_ptr(),

@@ -40,11 +40,13 @@ def validate_conditioned(dem: D.ArrayLike, nodata: Optional[float] = None) -> Tu
 
 
 def _validate(buf, ld, rows, cols, nodata, dev):
-    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
     has, nd = D.nodata_args(nodata)
     N.call("ht_d8_validate_conditioned_f32", buf.data_ptr(), rows, cols, ld, has, nd, 0, rows,
            0, 0, counts.data_ptr(), D.stream_ptr())
     c = counts.cpu()
+    if int(c[2]):
+        raise ValueError(f"{int(c[2])} cells have |elevation| >= 2**29 mm; not supported")
     return int(c[0]), int(c[1])
 
 
