@@ -143,12 +143,12 @@ class BandEngine:
         band.resolve(True)
         delivered, link = band.band_tables(mode)
         P = self.world
-        all_d = torch.empty((P,) + tuple(delivered.shape), dtype=delivered.dtype,
-                            device=delivered.device)
-        all_l = torch.empty((P,) + tuple(link.shape), dtype=link.dtype, device=link.device)
+        # (P*2, cols): concatenation along dim 0 is the layout every backend accepts
+        all_d = torch.empty((P * 2, self.cols), dtype=delivered.dtype, device=delivered.device)
+        all_l = torch.empty((P * 2, self.cols), dtype=link.dtype, device=link.device)
         dist.all_gather_into_tensor(all_d, delivered.contiguous(), group=self.group)
         dist.all_gather_into_tensor(all_l, link.contiguous(), group=self.group)
-        base, nxt = build_band_graph(all_d, all_l)
+        base, nxt = build_band_graph(all_d.view(P, 2, self.cols), all_l.view(P, 2, self.cols))
         inflow = band.forest_resolve(base, nxt, mode).view(P, 2, self.cols)
         band.add_inflow(inflow[self.rank, 0], inflow[self.rank, 1], mode)
         band.resolve(False)

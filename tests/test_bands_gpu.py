@@ -1,0 +1,107 @@
+"""GPU: row-band sharding on ONE device -- P CudaBand objects driven in-process
+through the same table / band-graph functions BandEngine uses, against the
+oracle on the whole raster.  (Ranks that wait on each other must not run as
+separate launches on one GPU, so the collective itself is covered by the gloo
+test on CPU and by the multi-GPU bench.)"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+ND = -32767.0
+
+
+def run_bands(dem, cuts, nodata, csx, csy, mode=0, weight=None):
+    from hydrotools.cuda import distributed as HD
+    total, cols = dem.shape
+    P = len(cuts) - 1
+    bands = []
+    for b in range(P):
+        lo, hi = cuts[b], cuts[b + 1]
+        band = HD.CudaBand(hi - lo, cols, lo, total, csx, csy, nodata,
+                           has_above=b > 0, has_below=b < P - 1)
+        band.load(dem[lo:hi])
+        if weight is not None:
+            band.set_weight(weight[lo:hi])
+        bands.append(band)
+    # halo exchange (2 rows), as BandEngine.exchange_halos does with send/recv
+    for b in range(P):
+        if b > 0:
+            bands[b].set_halo_rows(top=True, rows=bands[b - 1].edge_rows(top=False, depth=2))
+        if b < P - 1:
+            bands[b].set_halo_rows(top=False, rows=bands[b + 1].edge_rows(top=True, depth=2))
+    tabs = []
+    for band in bands:
+        band.direction()
+        band.local(mode)
+        band.resolve(True)
+        tabs.append(band.band_tables(mode))
+    all_d = torch.stack([t[0] for t in tabs])
+    all_l = torch.stack([t[1] for t in tabs])
+    base, nxt = HD.build_band_graph(all_d, all_l)
+    inflow = bands[0].forest_resolve(base, nxt, mode).view(P, 2, cols)
+    outs = []
+    for b, band in enumerate(bands):
+        band.add_inflow(inflow[b, 0], inflow[b, 1], mode)
+        band.resolve(False)
+        band.final(mode)
+        fd, fa = band.results()
+        outs.append((fd.cpu().numpy(), fa.cpu().numpy()))
+    return np.vstack([o[0] for o in outs]), np.vstack([o[1] for o in outs])
+
+
+@pytest.mark.parametrize("cuts", [[0, 150, 300], [0, 64, 128, 300], [0, 2, 100, 101 + 64, 300],
+                                  [0, 37, 38 + 37, 200, 300]])
+def test_bands_equal_oracle(hc, cuts):
+    dem = oracle.synth_dem(42, 300, 333, with_nulls=True)
+    fd, fa = run_bands(dem, cuts, ND, 10.0, 10.0)
+    efd, efa = oracle.rwatershed(dem, ND, 10.0, 10.0)
+    np.testing.assert_array_equal(fd, efd)
+    np.testing.assert_array_equal(fa, efa)
+
+
+def test_bands_long_rivers(hc):
+    """Rivers cross every band boundary; meanders re-enter bands."""
+    dem = oracle.synth_dem(20261019, 1500, 1100)
+    cuts = [0, 200, 500, 777, 1100, 1500]
+    fd, fa = run_bands(dem, cuts, None, 10.0, 10.0)
+    efd, efa = oracle.rwatershed(dem, None, 10.0, 10.0)
+    np.testing.assert_array_equal(fd, efd)
+    np.testing.assert_array_equal(fa, efa)
+
+
+def test_bands_upward_flow(hc):
+    """Flip the DEM so that water runs towards row 0: flow crosses band boundaries
+    upwards (virtual slots of the band above)."""
+    dem = np.ascontiguousarray(oracle.synth_dem(7, 400, 300, with_nulls=True)[::-1])
+    assert oracle.check_conditioned(dem, ND) == (0, 0)
+    fd, fa = run_bands(dem, [0, 130, 270, 400], ND, 10.0, 10.0)
+    efd, efa = oracle.rwatershed(dem, ND, 10.0, 10.0)
+    np.testing.assert_array_equal(fd, efd)
+    np.testing.assert_array_equal(fa, efa)
+
+
+def test_bands_weighted(hc):
+    dem = oracle.synth_dem(3, 500, 400, with_nulls=True)
+    w = oracle.synth_weight(3, 500, 400)
+    from hydrotools.cuda import _native as N
+    _, acc = run_bands(dem, [0, 100, 333, 500], ND, 10.0, 10.0, mode=N.MODE_WEIGHTED, weight=w)
+    # weighted accumulation follows r.watershed's graph here (edge cells do not pass
+    # flow on), so the expectation is built from the oracle's directions with the
+    # edge cells made terminal
+    efd, _ = oracle.rwatershed(dem, ND, 10.0, 10.0)
+    edge = np.zeros(dem.shape, bool)
+    null = dem == ND
+    edge[[0, -1], :] = True
+    edge[:, [0, -1]] = True
+    pad = np.pad(null, 1, constant_values=False)
+    for dr in (0, 1, 2):
+        for dc in (0, 1, 2):
+            edge |= pad[dr:dr + dem.shape[0], dc:dc + dem.shape[1]]
+    d = efd.copy()
+    d[edge & ~null] = 0
+    exp = oracle.flowacc(d, w)
+    m = ~np.isnan(exp)
+    np.testing.assert_allclose(acc[m], exp[m], rtol=1e-5, atol=0)
