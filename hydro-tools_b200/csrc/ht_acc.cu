@@ -75,8 +75,9 @@ struct AccArgs {
     int64_t packed_ld;
 };
 
-__device__ __forceinline__ int code_dr(int code) { return (int)((0x122210000ULL >> (4 * code)) & 0xF) - 1; }
-__device__ __forceinline__ int code_dc(int code) { return (int)((0x221000120ULL >> (4 * code)) & 0xF) - 1; }
+// row / column step of GRASS code 1..8 (2-bit tables: dr+1 = 0,0,0,1,2,2,2,1; dc+1 = 2,1,0,0,0,1,2,2)
+__device__ __forceinline__ int code_dr(int code) { return (int)((0x1A900u >> (2 * code)) & 3u) - 1; }
+__device__ __forceinline__ int code_dc(int code) { return (int)((0x29018u >> (2 * code)) & 3u) - 1; }
 // GRASS code that points at window cell k (3x3 row-major)
 __device__ __forceinline__ int win2code(int k) { return (int)((0x765804123ULL >> (4 * k)) & 0xF); }
 // r.watershed neighbour order S,N,W,E,NE,SW,SE,NW as window cells
@@ -419,9 +420,10 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 //            entry cell upstream; each entry's inflow is added along its path to
 //            the tile exit by an independent walker (no ordering needed).
 // ===========================================================================
-constexpr int16_t R_TERM = 0;       // no receiver
+// receiver offsets; everything >= R_EXIT is "the chain ends here"
 constexpr int16_t R_EXIT = 0x4000;  // receiver lies outside the tile
 constexpr int16_t R_NULL = 0x4001;  // NULL cell / outside the raster
+constexpr int16_t R_TERM = 0x4002;  // no receiver
 constexpr int SMC_ROFF = SM_EFF;                  // int16[T*T]
 constexpr int SMC_LO = SMC_ROFF + T * T * 2;      // uint32[T*T]
 constexpr int SMC_Q = SMC_LO + T * T * 4;         // uint16[T*T] queue of source cells
@@ -477,13 +479,16 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
 
     // ---- S1: receiver offset and weight of every tile cell
+    // (tiles whose ring lies wholly inside the band need no bounds tests)
+    const bool interior = rb.ry_lo == 0 && rb.ry_hi == RH - 1 && rb.rx_lo == XO - 1 &&
+                          rb.rx_hi == XO + T && th == T && tw == T;
 #pragma unroll 4
     for (int i = 0; i < CPT; i++) {
         const int c = tid + i * THREADS;
         const int ly = c >> 6, lx = c & (T - 1);
         const int yy = ly + 1, xx = lx + XO;
         const uint8_t b = pk[yy * RP + xx];
-        const bool ok = ly < th && lx < tw && !(b & HT_DIR_NULL);
+        const bool ok = (interior || (ly < th && lx < tw)) && !(b & HT_DIR_NULL);
         int16_t o = ok ? R_TERM : R_NULL;
         unsigned w = 0;
         if (ok) {
@@ -491,7 +496,9 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             const int code = b & HT_DIR_CODE;
             if (!(b & (HT_DIR_NEG | HT_DIR_EDGE)) && code >= 1 && code <= 8) {
                 const int dr = code_dr(code), dc = code_dc(code);
-                if (ring_valid(pk, rb, yy + dr, xx + dc)) {
+                const bool tv = interior ? !(pk[(yy + dr) * RP + xx + dc] & HT_DIR_NULL)
+                                         : ring_valid(pk, rb, yy + dr, xx + dc);
+                if (tv) {
                     const int ny = ly + dr, nx = lx + dc;
                     o = (ny >= 0 && ny < th && nx >= 0 && nx < tw) ? (int16_t)(dr * T + dc) : R_EXIT;
                 }
@@ -507,7 +514,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     for (int i = 0; i < CPT; i++) {
         const int c = tid + i * THREADS;
         const int16_t o = roff[c];
-        if (o != R_TERM && o < R_EXIT)
+        if (o < R_EXIT)
             atomicAdd(&lo32[c + o], 1u << 28);
     }
     __syncthreads();
@@ -544,18 +551,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                 v = lo32[cur] & 0x0FFFFFFFu;
             }
             const int16_t o = roff[cur];
-            if (o == R_TERM) {
-                cur = -1;
-                continue;
-            }
-            if (o == R_EXIT) {
-                // flow leaves the tile: feed the boundary graph
-                const int code = pk[((cur >> 6) + 1) * RP + (cur & (T - 1)) + XO] & HT_DIR_CODE;
-                const int64_t lr = y0 + (cur >> 6) + code_dr(code), gc = x0 + (cur & (T - 1)) + code_dc(code);
-                const int64_t s = lr < 0 ? vslot_of(p, false, gc)
-                                : lr >= p.rows ? vslot_of(p, true, gc)
-                                               : slot_of(p, lr, gc);
-                atomicAdd(reinterpret_cast<unsigned long long *>(p.base) + s, (unsigned long long)v);
+            if (o >= R_EXIT) { // chain ends in this tile (exits are flushed below)
                 cur = -1;
                 continue;
             }
@@ -570,6 +566,22 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         }
     }
     __syncthreads();
+
+    // ---- S3b: flow that leaves the tile feeds the boundary graph
+#pragma unroll 4
+    for (int i = 0; i < CPT; i++) {
+        const int c = tid + i * THREADS;
+        if (roff[c] != R_EXIT)
+            continue;
+        const int ly = c >> 6, lx = c & (T - 1);
+        const int code = pk[(ly + 1) * RP + lx + XO] & HT_DIR_CODE;
+        const int64_t lr = y0 + ly + code_dr(code), gc = x0 + lx + code_dc(code);
+        const int64_t s = lr < 0 ? vslot_of(p, false, gc)
+                        : lr >= p.rows ? vslot_of(p, true, gc)
+                                       : slot_of(p, lr, gc);
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.base) + s,
+                  (unsigned long long)(lo32[c] & 0x0FFFFFFFu));
+    }
 
     // ---- S4a: where does the path of each entry cell leave the tile?
     {
@@ -595,7 +607,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                 slot = slot_of(p, y0 + ly, x0 + lx);
                 int cur = ly * T + lx;
                 int16_t o;
-                while ((o = roff[cur]) != R_TERM && o < R_EXIT)
+                while ((o = roff[cur]) < R_EXIT)
                     cur += o;
                 if (o == R_EXIT) {
                     const int code = pk[((cur >> 6) + 1) * RP + (cur & (T - 1)) + XO] & HT_DIR_CODE;
@@ -609,13 +621,17 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         publish_entry(p, entry, slot, nxt);
     }
 
-    // ---- S4b: tile-local counts for stage C
+    // ---- S4b: tile-local counts for stage C (thread -> one column, every 4th row)
+    {
+        const int lx = tid & (T - 1), ly0 = tid >> 6;
+        uint16_t *dst = p.lacc + (y0 + ly0) * p.lacc_ld + x0 + lx;
+        const int64_t step = 4 * p.lacc_ld;
+        if (lx < tw) {
 #pragma unroll 4
-    for (int i = 0; i < CPT; i++) {
-        const int c = tid + i * THREADS;
-        const int ly = c >> 6, lx = c & (T - 1);
-        if (ly < th && lx < tw)
-            p.lacc[(y0 + ly) * p.lacc_ld + x0 + lx] = (uint16_t)lo32[c];
+            for (int i = 0; i < CPT; i++, dst += step)
+                if (ly0 + 4 * i < th)
+                    *dst = (uint16_t)lo32[tid + i * THREADS];
+        }
     }
 }
 
@@ -645,13 +661,16 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         ht::tma_load_2d(pk, &map, (int)x0, (int)y0 + p.halo_top, &bar);
     }
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
-    // tile-local counts while the TMA is in flight
+    // tile-local counts while the TMA is in flight (thread -> one column, every 4th row)
+    const int mx = tid & (T - 1), my0 = tid >> 6;
+    {
+        const uint16_t *src = p.lacc + (y0 + my0) * p.lacc_ld + x0 + mx;
+        const int64_t step = 4 * p.lacc_ld;
 #pragma unroll 4
-    for (int i = 0; i < CPT; i++) {
-        const int c = tid + i * THREADS;
-        const int ly = c >> 6, lx = c & (T - 1);
-        lo32[c] = (ly < th && lx < tw) ? p.lacc[(y0 + ly) * p.lacc_ld + x0 + lx] : 0u;
-        hi32[c] = 0u;
+        for (int i = 0; i < CPT; i++, src += step) {
+            lo32[tid + i * THREADS] = (mx < tw && my0 + 4 * i < th) ? (unsigned)*src : 0u;
+            hi32[tid + i * THREADS] = 0u;
+        }
     }
     __syncthreads();
     ht::mbar_wait(&bar, 0);
@@ -686,19 +705,23 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     __syncthreads();
 
     // ---- outputs
+    if (mx >= tw)
+        return;
+    double *accp = p.acc ? p.acc + (y0 + my0) * p.acc_ld + x0 + mx : nullptr;
+    int8_t *dirp = (WMODE == W_ONE && p.dir_out) ? p.dir_out + (y0 + my0) * p.dir_ld + x0 + mx : nullptr;
 #pragma unroll 2
     for (int i = 0; i < CPT; i++) {
         const int c = tid + i * THREADS;
-        const int ly = c >> 6, lx = c & (T - 1);
-        if (ly >= th || lx >= tw)
-            continue;
+        const int ly = my0 + 4 * i, lx = mx;
+        if (ly >= th)
+            break;
         const uint8_t b = pk[c];
         const bool null = b & HT_DIR_NULL;
         const unsigned long long cnt = ((unsigned long long)hi32[c] << 20) + lo32[c];
         const double a = (double)cnt;
-        if (p.acc)
-            p.acc[(y0 + ly) * p.acc_ld + x0 + lx] = null ? __longlong_as_double(0x7ff8000000000000LL) : a;
-        if (WMODE == W_ONE && p.dir_out) {
+        if (accp)
+            accp[(int64_t)(4 * i) * p.acc_ld] = null ? __longlong_as_double(0x7ff8000000000000LL) : a;
+        if (dirp) {
             const int code = b & HT_DIR_CODE;
             int out;
             if (null)
@@ -726,7 +749,7 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             }
             else
                 out = code;
-            p.dir_out[(y0 + ly) * p.dir_ld + x0 + lx] = (int8_t)out;
+            dirp[(int64_t)(4 * i) * p.dir_ld] = (int8_t)out;
         }
     }
 }
@@ -734,74 +757,116 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // ---------------------------------------------------------------------------
 // stage B: boundary-graph resolve (subtree sums over a forest) by pointer doubling
 // ---------------------------------------------------------------------------
+// Grid-wide barrier for the cooperative launch below (all CTAs co-resident):
+// a monotonic arrival counter; barrier number k releases at (k+1) * gridDim.x.
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned target = (++epoch) * gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    else
+        ++epoch;
+    __syncthreads();
+}
+
 template <typename V>
-__global__ void __launch_bounds__(256)
-coarse_resolve_kernel(const V *base0, const int32_t *next0, V *aggA, V *aggB, int32_t *ptrA,
+__global__ void __launch_bounds__(256, 4)
+coarse_resolve_kernel(const V *base0, const int32_t *next0, V *agg, V *delta, int32_t *ptrA,
                       int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n,
                       const int32_t *list, const int *nlist, int *flags, int *rounds_out)
 {
-    cg::grid_group grid = cg::this_grid();
+    unsigned *gbar = reinterpret_cast<unsigned *>(flags + 96); // zeroed with flags
+    unsigned epoch = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // only the slots in `list` are nodes (all n slots if there is no list)
     const int64_t na = list ? (int64_t)*nlist : n;
-    // the graph itself (base0 / next0) is left untouched so that it can be
-    // resolved again after inflow from other bands has been added
+    // The graph itself (base0 / next0) is left untouched so that it can be resolved
+    // again after inflow from other bands has been added.  `delta` arrives zeroed.
     if (rootA)
         for (int64_t u = t0; u < n; u += stride)
             rootB[u] = (int32_t)u; // slots that are not nodes end at themselves
     for (int64_t i = t0; i < na; i += stride) {
         const int64_t u = list ? list[i] : i;
-        aggA[u] = base0[u];
+        agg[u] = base0[u];
         ptrA[u] = next0[u];
         if (rootA)
             rootA[u] = (int32_t)u;
     }
-    grid.sync();
+    grid_barrier(gbar, epoch);
+    // round k: agg[v] holds the sum over the nodes within 2^k - 1 steps upstream of v
+    // (v included), ptr[u] the node 2^k steps downstream of u.
+    //   phase 1: every u hands agg[u] to ptr[u] through `delta`, ptr[u] <- ptr[ptr[u]]
+    //   phase 2: agg += delta, delta <- 0
     int round = 0;
     for (;; round++) {
-        // agg_{k+1} starts as agg_k
-        for (int64_t i = t0; i < na; i += stride) {
-            const int64_t u = list ? list[i] : i;
-            aggB[u] = aggA[u];
-        }
-        grid.sync();
         bool any = false;
-        for (int64_t i = t0; i < na; i += stride) {
-            const int64_t u = list ? list[i] : i;
-            const int32_t q = ptrA[u];
-            if (q >= 0) {
-                const V a = aggA[u];
-                if (a != (V)0)
-                    atomic_add_v(&aggB[q], a);
-                ptrB[u] = ptrA[q];
-                if (rootA)
-                    rootB[u] = rootA[q];
-                any = true;
+        constexpr int U = 4; // independent nodes in flight per thread
+        for (int64_t i0 = t0; i0 < na; i0 += stride * U) {
+            int32_t u[U], q[U], qq[U], rr[U];
+            V a[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const int64_t i = i0 + j * stride;
+                u[j] = i < na ? (list ? list[i] : (int32_t)i) : -1;
             }
-            else {
-                ptrB[u] = q;
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                q[j] = u[j] >= 0 ? ptrA[u[j]] : -1;
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                qq[j] = q[j] >= 0 ? ptrA[q[j]] : q[j];
+                a[j] = q[j] >= 0 ? agg[u[j]] : (V)0;
                 if (rootA)
-                    rootB[u] = rootA[u];
+                    rr[j] = u[j] >= 0 ? rootA[q[j] >= 0 ? q[j] : u[j]] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                if (u[j] < 0)
+                    continue;
+                if (q[j] >= 0) {
+                    if (a[j] != (V)0)
+                        atomic_add_v(&delta[q[j]], a[j]);
+                    any = true;
+                }
+                ptrB[u[j]] = qq[j];
+                if (rootA)
+                    rootB[u[j]] = rr[j];
             }
         }
         if (any)
             flags[round] = 1;
-        grid.sync();
-        V *ta = aggA; aggA = aggB; aggB = ta;
+        grid_barrier(gbar, epoch);
+        const bool more = flags[round] != 0;
+        if (more) {
+            for (int64_t i = t0; i < na; i += stride) {
+                const int64_t u = list ? list[i] : i;
+                const V d = delta[u];
+                if (d != (V)0) {
+                    agg[u] += d;
+                    delta[u] = (V)0;
+                }
+            }
+        }
         int32_t *tp = ptrA; ptrA = ptrB; ptrB = tp;
         tp = rootA; rootA = rootB; rootB = tp;
-        if (!flags[round] || round == 62)
+        if (!more || round == 62)
             break;
+        grid_barrier(gbar, epoch);
     }
-    // round + 1 rounds were run; an odd count leaves the result in the caller's "B"
-    // buffers already, an even count leaves it in "A"
-    if (round & 1) {
+    // the caller reads the last node of every path from its "rootB": after
+    // round + 1 swaps that is the local rootA when the count is odd
+    if (rootA && (round & 1)) {
         for (int64_t i = t0; i < na; i += stride) {
             const int64_t u = list ? list[i] : i;
-            aggB[u] = aggA[u];
-            if (rootA)
-                rootB[u] = rootA[u];
+            rootB[u] = rootA[u];
         }
     }
     if (t0 == 0 && rounds_out)
@@ -916,7 +981,7 @@ int dispatch_tile(int mode, const CUtensorMap &map, const AccArgs &p, cudaStream
 }
 
 template <typename V>
-int launch_resolve(const void *base0, const int32_t *next0, void *aggA_, void *aggB_,
+int launch_resolve(const void *base0, const int32_t *next0, void *agg_, void *delta_,
                    int32_t *ptrA, int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n,
                    const int32_t *list, const int *nlist, int *flags, int *rounds_dev,
                    cudaStream_t st)
@@ -929,14 +994,17 @@ int launch_resolve(const void *base0, const int32_t *next0, void *aggA_, void *a
     int dev = 0, sms = 0;
     HT_CUDA_TRY(cudaGetDevice(&dev));
     HT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int grid = sms * (per_sm > 4 ? 4 : per_sm);
+    int grid = sms * per_sm;
     const int64_t need = (n + 255) / 256;
     if (grid > need)
         grid = (int)(need > 0 ? need : 1);
-    HT_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+    HT_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));      // per-round flags
+    HT_CUDA_TRY(cudaMemsetAsync(flags + 96, 0, sizeof(int), st));      // grid barrier counter
     const V *b0 = (const V *)base0;
-    V *aggA = (V *)aggA_, *aggB = (V *)aggB_;
-    void *args[] = {&b0, &next0, &aggA, &aggB, &ptrA, &ptrB, &rootA, &rootB, &n, &list, &nlist, &flags, &rounds_dev};
+    // result lands in `agg`; `delta` is scratch and must start at zero
+    HT_CUDA_TRY(cudaMemsetAsync(delta_, 0, n * 8, st));
+    V *agg = (V *)agg_, *delta = (V *)delta_;
+    void *args[] = {&b0, &next0, &agg, &delta, &ptrA, &ptrB, &rootA, &rootB, &n, &list, &nlist, &flags, &rounds_dev};
     HT_CUDA_TRY(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(256), args, 0, st));
     return 0;
 }
@@ -1022,10 +1090,10 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
     int32_t *rA = want_roots ? wk.rootA : nullptr, *rB = want_roots ? wk.rootB : nullptr;
     HT_CUDA_TRY(cudaMemsetAsync(wk.aggB, 0, wk.nslots * 8, (cudaStream_t)stream));
     if (mode == W_F32)
-        return launch_resolve<double>(wk.base0, wk.next0, wk.aggA, wk.aggB, wk.ptrA, wk.ptrB, rA,
+        return launch_resolve<double>(wk.base0, wk.next0, wk.aggB, wk.aggA, wk.ptrA, wk.ptrB, rA,
                                       rB, wk.nslots, wk.list, wk.nlist, wk.flags, rounds_dev,
                                       (cudaStream_t)stream);
-    return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.aggA, wk.aggB, wk.ptrA,
+    return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.aggB, wk.aggA, wk.ptrA,
                                               wk.ptrB, rA, rB, wk.nslots, wk.list, wk.nlist,
                                               wk.flags, rounds_dev, (cudaStream_t)stream);
 }
@@ -1072,9 +1140,9 @@ extern "C" int ht_forest_resolve(const void *base, const int32_t *next, int64_t 
     int32_t *ptrB = (int32_t *)b; b += align_up(n * 4);
     int *flags = (int *)b;
     if (is_f64)
-        return launch_resolve<double>(base, next, aggA, agg_out, ptrA, ptrB, nullptr, nullptr, n,
+        return launch_resolve<double>(base, next, agg_out, aggA, ptrA, ptrB, nullptr, nullptr, n,
                                       nullptr, nullptr, flags, nullptr, (cudaStream_t)stream);
-    return launch_resolve<unsigned long long>(base, next, aggA, agg_out, ptrA, ptrB, nullptr, nullptr,
+    return launch_resolve<unsigned long long>(base, next, agg_out, aggA, ptrA, ptrB, nullptr, nullptr,
                                               n, nullptr, nullptr, flags, nullptr, (cudaStream_t)stream);
 }
 

@@ -207,6 +207,13 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
         const int ay_hi = (int)min((int64_t)BH - 1, p.rows + p.halo_bot - 1 - y0 + 2);
         const int ax_lo = (int)max((int64_t)0, PADL - x0);
         const int ax_hi = (int)min((int64_t)BW - 1, p.cols - 1 - x0 + PADL);
+        // ring coordinates (yy, xx) of the raster's border rows / columns, if they
+        // fall into this tile's ring (else an index no cell has)
+        const int64_t gy0 = p.row0 + y0 - 1, gx0 = x0 - 1; // raster coords of ring (0, 0)
+        const int yy_top = (int)max((int64_t)-1, min((int64_t)DH, -gy0));
+        const int yy_bot = (int)max((int64_t)-1, min((int64_t)DH, p.total_rows - 1 - gy0));
+        const int xx_left = (int)max((int64_t)-1, min((int64_t)DW, -gx0));
+        const int xx_right = (int)max((int64_t)-1, min((int64_t)DW, p.cols - 1 - gx0));
         if (tid == 0)
             any_edge = 0;
         ht::mbar_wait(&full[s], (k / STAGES) & 1);
@@ -234,9 +241,8 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
         for (int i = tid; i < DW * DH; i += THREADS) {
             const int yy = i / DW, xx = i - yy * DW; // ring coords; box coords +1, +PADL-1
             const int32_t *a = alt + (yy + 1) * BW + (xx + PADL - 1);
-            const int64_t gr = p.row0 + y0 - 1 + yy, gc = x0 - 1 + xx;
-            const bool border = gr == 0 || gc == 0 || gr == p.total_rows - 1 || gc == p.cols - 1;
-            const int border_code = gr == 0 ? 2 : gc == 0 ? 4 : gr == p.total_rows - 1 ? 6 : 8;
+            const bool border = yy == yy_top || xx == xx_left || yy == yy_bot || xx == xx_right;
+            const int border_code = yy == yy_top ? 2 : xx == xx_left ? 4 : yy == yy_bot ? 6 : 8;
             unsigned pp = 0, tt = 0;
             const uint8_t b = d8_cell<VALIDATE>(a[-BW - 1], a[-BW], a[-BW + 1], a[-1], a[0], a[1],
                                                 a[BW - 1], a[BW], a[BW + 1], border, border_code,
@@ -246,7 +252,7 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             if (VALIDATE) {
                 // only cells of the tile itself are counted
                 const bool own = yy >= 1 && yy <= TH && xx >= 1 && xx <= TW &&
-                                 y0 - 1 + yy < p.rows && gc < p.cols;
+                                 y0 - 1 + yy < p.rows && x0 - 1 + xx < p.cols;
                 if (own) {
                     pits += pp;
                     ties += tt;
