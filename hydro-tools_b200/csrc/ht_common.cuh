@@ -147,14 +147,14 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
 __device__ __forceinline__ float fast_sqrt(float x)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
 __device__ __forceinline__ float fast_rcp(float x)
 {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 

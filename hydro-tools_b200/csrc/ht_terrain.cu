@@ -11,6 +11,8 @@
 // 128-bit streaming stores.  HBM-bound by design: 4 B read + 12 B written per
 // cell (16 B/cell algorithmic); fp32 math with MUFU sqrt/rcp and a degree-6
 // minimax atan core (relative error < 1e-6, inside the 1e-5 contract).
+#include <math.h>
+
 #include "ht_common.cuh"
 
 namespace {
@@ -33,6 +35,7 @@ struct TerrainArgs {
     int tiles_x, tiles_y;
     int has_nodata, nodata_is_nan;
     float nodata;
+    float nd_lo, nd_hi;  // closed interval of floats that ARE_REAL_EQUAL to nodata
     float inv_ew, inv_ns, inv_8scale;
     int percent;
     float *slope, *aspect, *tri;
@@ -40,21 +43,25 @@ struct TerrainArgs {
 };
 
 // ARE_REAL_EQUAL(v, nodata) of gdal_priv.h (== or within 2 float ulps); NaN
-// nodata -> isnan (rule G2)
-__device__ __forceinline__ bool is_nd(float v, float nd, int nd_is_nan)
+// nodata -> isnan (rule G2).  The set of floats equal to nodata in that sense is
+// an interval around it, found once on the host (nodata_interval).
+__host__ __device__ __forceinline__ bool are_real_equal(float a, float b)
 {
-    if (nd_is_nan)
+    return a == b || fabsf(a - b) < 1.1920929e-07f * fabsf(a + b) * 2.0f;
+}
+
+__device__ __forceinline__ bool is_nd(float v, const TerrainArgs &p)
+{
+    if (p.nodata_is_nan)
         return v != v;
-    return v == nd || fabsf(v - nd) < 1.1920929e-07f * fabsf(v + nd) * 2.0f;
+    return v >= p.nd_lo && v <= p.nd_hi;
 }
 
 // INTERPOL(a, b) of gdaldem_lib.cpp (rule G3)
-__device__ __forceinline__ float interpol(float a, float b, int has_nd, float nd,
-                                          int nd_is_nan)
+__device__ __forceinline__ float interpol(float a, float b, const TerrainArgs &p)
 {
-    if (has_nd && !nd_is_nan &&
-        (is_nd(a, nd, 0) || is_nd(b, nd, 0)))
-        return nd;
+    if (p.has_nodata && !p.nodata_is_nan && (is_nd(a, p) || is_nd(b, p)))
+        return p.nodata;
     return 2.0f * a - b; // NaN nodata propagates as NaN by itself
 }
 
@@ -174,13 +181,13 @@ __device__ __forceinline__ Row6 load_row(const float *srow, int lane,
     if (ND) {
 #pragma unroll
         for (int k = 0; k < 6; k++)
-            r.nd |= is_nd(r.v[k], p.nodata, p.nodata_is_nan) ? (1u << k) : 0u;
+            r.nd |= is_nd(r.v[k], p) ? (1u << k) : 0u;
     }
     return r;
 }
 
 template <bool ND, bool WS, bool WA, bool WT>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 3)
 terrain_kernel(const __grid_constant__ CUtensorMap map, const TerrainArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -235,24 +242,20 @@ terrain_kernel(const __grid_constant__ CUtensorMap map, const TerrainArgs p)
             if (left_edge)
                 for (int yy = yy_lo + tid; yy <= yy_hi; yy += THREADS)
                     sm[yy * BW + PADL - 1] =
-                        interpol(sm[yy * BW + PADL], sm[yy * BW + PADL + 1],
-                                 p.has_nodata, p.nodata, p.nodata_is_nan);
+                        interpol(sm[yy * BW + PADL], sm[yy * BW + PADL + 1], p);
             if (right_edge)
                 for (int yy = yy_lo + tid; yy <= yy_hi; yy += THREADS)
                     sm[yy * BW + xx_last + 1] =
-                        interpol(sm[yy * BW + xx_last], sm[yy * BW + xx_last - 1],
-                                 p.has_nodata, p.nodata, p.nodata_is_nan);
+                        interpol(sm[yy * BW + xx_last], sm[yy * BW + xx_last - 1], p);
             const int xx_lo = left_edge ? PADL : 0;
             const int xx_hi = right_edge ? xx_last : BW - 1;
             if (top_edge)
                 for (int xx = xx_lo + tid; xx <= xx_hi; xx += THREADS)
-                    sm[xx] = interpol(sm[BW + xx], sm[2 * BW + xx], p.has_nodata,
-                                      p.nodata, p.nodata_is_nan);
+                    sm[xx] = interpol(sm[BW + xx], sm[2 * BW + xx], p);
             if (bot_edge)
                 for (int xx = xx_lo + tid; xx <= xx_hi; xx += THREADS)
                     sm[(yy_last + 1) * BW + xx] =
-                        interpol(sm[yy_last * BW + xx], sm[(yy_last - 1) * BW + xx],
-                                 p.has_nodata, p.nodata, p.nodata_is_nan);
+                        interpol(sm[yy_last * BW + xx], sm[(yy_last - 1) * BW + xx], p);
             __syncthreads();
         }
 
@@ -334,18 +337,18 @@ __global__ void terrain_corner_kernel(const float *dem, int64_t ld, const Terrai
     float w[9];
     for (int k = 0; k < 3; k++) {
         const float a = dem[i * ld + jj[k]], b = dem[inb * ld + jj[k]];
-        const float e = interpol(a, b, p.has_nodata, p.nodata, p.nodata_is_nan);
+        const float e = interpol(a, b, p);
         if (top) { w[k] = e; w[3 + k] = a; w[6 + k] = b; }
         else     { w[k] = b; w[3 + k] = a; w[6 + k] = e; }
     }
     Out3 o;
-    if (ND && is_nd(w[4], p.nodata, p.nodata_is_nan)) {
+    if (ND && is_nd(w[4], p)) {
         o.s = o.a = o.t = HT_TERRAIN_NODATA;
     }
     else {
         if (ND)
             for (int k = 0; k < 9; k++)
-                if (is_nd(w[k], p.nodata, p.nodata_is_nan))
+                if (is_nd(w[k], p))
                     w[k] = w[4];
         o = horn<true, true, true>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], p);
     }
@@ -370,7 +373,7 @@ int launch(const CUtensorMap &map, const TerrainArgs &p, cudaStream_t st)
     const size_t smem = (size_t)STAGES * STAGE_STRIDE;
     HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = p.tiles_x * p.tiles_y;
-    int grid = 2 * ht::kSMs; // two resident CTAs per SM, persistent
+    int grid = 3 * ht::kSMs; // three resident CTAs per SM, persistent
     if (grid > ntiles)
         grid = ntiles;
     kern<<<grid, THREADS, smem, st>>>(map, p);
@@ -430,6 +433,18 @@ extern "C" int ht_terrain_fused_f32(const float *dem, int64_t rows, int64_t cols
     p.has_nodata = has_nodata ? 1 : 0;
     p.nodata = nodata;
     p.nodata_is_nan = (has_nodata && nodata != nodata) ? 1 : 0;
+    p.nd_lo = p.nd_hi = nodata;
+    if (has_nodata && !p.nodata_is_nan && !isinf(nodata)) {
+        // widen ulp by ulp while ARE_REAL_EQUAL still holds (a handful of steps)
+        for (int i = 0; i < 64; i++) {
+            const float lo = nextafterf(p.nd_lo, -INFINITY), hi = nextafterf(p.nd_hi, INFINITY);
+            bool grew = false;
+            if (!isinf(lo) && are_real_equal(lo, nodata)) { p.nd_lo = lo; grew = true; }
+            if (!isinf(hi) && are_real_equal(hi, nodata)) { p.nd_hi = hi; grew = true; }
+            if (!grew)
+                break;
+        }
+    }
     p.inv_ew = (float)(1.0 / ewres);
     p.inv_ns = (float)(1.0 / nsres);
     p.inv_8scale = (float)(1.0 / (8.0 * zscale));
