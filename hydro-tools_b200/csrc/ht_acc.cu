@@ -414,7 +414,7 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // Count modes (cell counts, taint counts): lean integer kernels.
 //   stage A  acc_local_cnt_kernel : receiver offsets -> scatter in-degree ->
 //            flattened chain walk with ONE shared atomic per edge (the 32-bit
-//            word carries [donors to come : 4 | value : 28]); writes the
+//            word carries [donors to come : 4 | link code : 4 | value : 24]); writes the
 //            tile-local count of every cell (<= 4096, u16) for stage C.
 //   stage C  acc_final_cnt_kernel : final = tile-local count + inflow of every
 //            entry cell upstream; each entry's inflow is added along its path to
@@ -431,6 +431,14 @@ constexpr int SMC_BAR = SMC_Q + T * T * 2;        // mbarrier, then queue head /
 constexpr int SMC_TOTAL = SMC_BAR + 32;
 
 struct RingBounds { int ry_lo, ry_hi, rx_lo, rx_hi; }; // usable ring-tile cells (inclusive)
+
+// offset (dr * T + dc) of GRASS code 1..8 inside the T x T tile arrays, from a
+// packed table of signed bytes: codes 1-4 = -63, -64, -65, -1; 5-8 = 63, 64, 65, 1
+__device__ __forceinline__ int link_offset(unsigned code)
+{
+    const unsigned tab = code <= 4u ? 0xFFBFC0C1u : 0x0141403Fu;
+    return (int)(signed char)(tab >> (8u * ((code - 1u) & 3u)));
+}
 
 __device__ __forceinline__ RingBounds ring_bounds(const AccArgs &p, int64_t x0, int64_t y0)
 {
@@ -500,7 +508,12 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                                          : ring_valid(pk, rb, yy + dr, xx + dc);
                 if (tv) {
                     const int ny = ly + dr, nx = lx + dc;
-                    o = (ny >= 0 && ny < th && nx >= 0 && nx < tw) ? (int16_t)(dr * T + dc) : R_EXIT;
+                    if (ny >= 0 && ny < th && nx >= 0 && nx < tw) {
+                        o = (int16_t)(dr * T + dc);
+                        w |= (unsigned)code << 24; // the word carries its own link
+                    }
+                    else
+                        o = R_EXIT;
                 }
             }
         }
@@ -541,27 +554,31 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     {
         const int qn = qctl[1];
         int cur = -1;
-        unsigned v = 0;
+        unsigned v = 0, word = 0;
         for (;;) {
             if (cur < 0) {
                 const int qi = atomicAdd(&qctl[0], 1);
                 if (qi >= qn)
                     break;
                 cur = queue[qi];
-                v = lo32[cur] & 0x0FFFFFFFu;
+                word = lo32[cur];
+                v = word & 0x00FFFFFFu;
             }
-            const int16_t o = roff[cur];
-            if (o >= R_EXIT) { // chain ends in this tile (exits are flushed below)
+            // the receiver's word (returned by the atomic) names the next link, so a
+            // step is one shared-memory round trip
+            const unsigned code = (word >> 24) & 0xFu;
+            if (!code) { // chain ends in this tile (exits are flushed below)
                 cur = -1;
                 continue;
             }
-            const int rc = cur + o;
+            const int rc = cur + link_offset(code);
             const unsigned old = atomicAdd(&lo32[rc], v + 0xF0000000u);
             if ((old >> 28) != 1u) {
                 cur = -1; // other donors still to come; the last one continues
                 continue;
             }
-            v += old & 0x0FFFFFFFu;
+            v += old & 0x00FFFFFFu;
+            word = old;
             cur = rc;
         }
     }
@@ -580,7 +597,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                         : lr >= p.rows ? vslot_of(p, true, gc)
                                        : slot_of(p, lr, gc);
         atomicAdd(reinterpret_cast<unsigned long long *>(p.base) + s,
-                  (unsigned long long)(lo32[c] & 0x0FFFFFFFu));
+                  (unsigned long long)(lo32[c] & 0x00FFFFFFu));
     }
 
     // ---- S4a: where does the path of each entry cell leave the tile?

@@ -186,6 +186,58 @@ __device__ __forceinline__ Row6 load_row(const float *srow, int lane,
     return r;
 }
 
+// Stencil over one staged tile: warp -> 4 rows, lane -> 4 columns.
+template <bool ND, bool WS, bool WA, bool WT>
+__device__ __forceinline__ void stencil_tile(const float *sm, int warp, int lane, int64_t x0,
+                                             int64_t y0, const TerrainArgs &p)
+{
+    const int yyc = 1 + 4 * warp; // smem row of the first centre row
+    Row6 ra = load_row<ND>(sm + (yyc - 1) * BW, lane, p);
+    Row6 rb = load_row<ND>(sm + yyc * BW, lane, p);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const Row6 rc = load_row<ND>(sm + (yyc + 1 + i) * BW, lane, p);
+        const int64_t gr = y0 + 4 * warp + i;
+        float os[4], oa[4], ot[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float w0 = ra.v[c], w1 = ra.v[c + 1], w2 = ra.v[c + 2];
+            float w3 = rb.v[c], w4 = rb.v[c + 1], w5 = rb.v[c + 2];
+            float w6 = rc.v[c], w7 = rc.v[c + 1], w8 = rc.v[c + 2];
+            bool centre_nd = false;
+            if (ND) {
+                centre_nd = (rb.nd >> (c + 1)) & 1u;
+                const unsigned ma = ra.nd >> c, mb = rb.nd >> c, mc = rc.nd >> c;
+                w0 = (ma & 1u) ? w4 : w0; w1 = (ma & 2u) ? w4 : w1; w2 = (ma & 4u) ? w4 : w2;
+                w3 = (mb & 1u) ? w4 : w3;                           w5 = (mb & 4u) ? w4 : w5;
+                w6 = (mc & 1u) ? w4 : w6; w7 = (mc & 2u) ? w4 : w7; w8 = (mc & 4u) ? w4 : w8;
+            }
+            Out3 o = horn<WS, WA, WT>(w0, w1, w2, w3, w4, w5, w6, w7, w8, p);
+            if (ND && centre_nd)
+                o.s = o.a = o.t = HT_TERRAIN_NODATA;
+            os[c] = o.s; oa[c] = o.a; ot[c] = o.t;
+        }
+        const int64_t gc = x0 + 4 * lane;
+        if (gr < p.rows && gc < p.cols) {
+            const int64_t off = gr * p.out_ld + gc;
+            if (gc + 3 < p.cols) {
+                if (WS) ht::st_stream_f4(p.slope + off, make_float4(os[0], os[1], os[2], os[3]));
+                if (WA) ht::st_stream_f4(p.aspect + off, make_float4(oa[0], oa[1], oa[2], oa[3]));
+                if (WT) ht::st_stream_f4(p.tri + off, make_float4(ot[0], ot[1], ot[2], ot[3]));
+            }
+            else {
+                for (int c = 0; c < 4 && gc + c < p.cols; c++) {
+                    if (WS) p.slope[off + c] = os[c];
+                    if (WA) p.aspect[off + c] = oa[c];
+                    if (WT) p.tri[off + c] = ot[c];
+                }
+            }
+        }
+        ra = rb;
+        rb = rc;
+    }
+}
+
 template <bool ND, bool WS, bool WA, bool WT>
 __global__ void __launch_bounds__(THREADS, 3)
 terrain_kernel(const __grid_constant__ CUtensorMap map, const TerrainArgs p)
@@ -259,52 +311,18 @@ terrain_kernel(const __grid_constant__ CUtensorMap map, const TerrainArgs p)
             __syncthreads();
         }
 
-        // ---- stencil: warp -> 4 rows, lane -> 4 columns
-        const int yyc = 1 + 4 * warp; // smem row of the first centre row
-        Row6 ra = load_row<ND>(sm + (yyc - 1) * BW, lane, p);
-        Row6 rb = load_row<ND>(sm + yyc * BW, lane, p);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const Row6 rc = load_row<ND>(sm + (yyc + 1 + i) * BW, lane, p);
-            const int64_t gr = y0 + 4 * warp + i;
-            float os[4], oa[4], ot[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                float w0 = ra.v[c], w1 = ra.v[c + 1], w2 = ra.v[c + 2];
-                float w3 = rb.v[c], w4 = rb.v[c + 1], w5 = rb.v[c + 2];
-                float w6 = rc.v[c], w7 = rc.v[c + 1], w8 = rc.v[c + 2];
-                bool centre_nd = false;
-                if (ND) {
-                    centre_nd = (rb.nd >> (c + 1)) & 1u;
-                    const unsigned ma = ra.nd >> c, mb = rb.nd >> c, mc = rc.nd >> c;
-                    w0 = (ma & 1u) ? w4 : w0; w1 = (ma & 2u) ? w4 : w1; w2 = (ma & 4u) ? w4 : w2;
-                    w3 = (mb & 1u) ? w4 : w3;                           w5 = (mb & 4u) ? w4 : w5;
-                    w6 = (mc & 1u) ? w4 : w6; w7 = (mc & 2u) ? w4 : w7; w8 = (mc & 4u) ? w4 : w8;
-                }
-                Out3 o = horn<WS, WA, WT>(w0, w1, w2, w3, w4, w5, w6, w7, w8, p);
-                if (ND && centre_nd)
-                    o.s = o.a = o.t = HT_TERRAIN_NODATA;
-                os[c] = o.s; oa[c] = o.a; ot[c] = o.t;
-            }
-            const int64_t gc = x0 + 4 * lane;
-            if (gr < p.rows && gc < p.cols) {
-                const int64_t off = gr * p.out_ld + gc;
-                if (gc + 3 < p.cols) {
-                    if (WS) ht::st_stream_f4(p.slope + off, make_float4(os[0], os[1], os[2], os[3]));
-                    if (WA) ht::st_stream_f4(p.aspect + off, make_float4(oa[0], oa[1], oa[2], oa[3]));
-                    if (WT) ht::st_stream_f4(p.tri + off, make_float4(ot[0], ot[1], ot[2], ot[3]));
-                }
-                else {
-                    for (int c = 0; c < 4 && gc + c < p.cols; c++) {
-                        if (WS) p.slope[off + c] = os[c];
-                        if (WA) p.aspect[off + c] = oa[c];
-                        if (WT) p.tri[off + c] = ot[c];
-                    }
-                }
-            }
-            ra = rb;
-            rb = rc;
+        // ---- stencil; tiles that hold no nodata at all take the plain path
+        if (ND) {
+            bool mine = false;
+            for (int i = tid; i < BW * BH; i += THREADS)
+                mine |= is_nd(sm[i], p);
+            if (__syncthreads_or(mine))
+                stencil_tile<true, WS, WA, WT>(sm, warp, lane, x0, y0, p);
+            else
+                stencil_tile<false, WS, WA, WT>(sm, warp, lane, x0, y0, p);
         }
+        else
+            stencil_tile<false, WS, WA, WT>(sm, warp, lane, x0, y0, p);
 
         // ---- recycle the stage: everyone is done reading (and patching) it
         ht::fence_proxy_async();
