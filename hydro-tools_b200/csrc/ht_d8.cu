@@ -16,9 +16,16 @@
 //
 // Kernel: persistent CTAs, 2-stage TMA pipeline of (32+4) x (128+8) fp32 tiles
 // (2-cell halo: the taint flag of a cell needs its neighbours' directions).
-// Pass 0 converts the tile in place to GRASS integer millimetres, pass 1
-// computes the packed direction byte of the (32+2) x (128+2) inner cells into
-// shared memory, pass 2 adds the taint flag and writes 128-bit rows.
+// Pass 0 converts the tile in place to GRASS integer millimetres, held as
+// integer-valued floats (|alt| < 2^24 mm, so every difference is exact in fp32).
+//  * plain tiles (no NULL cell in the box, no raster border, not the first /
+//    last tile row of a band): every thread owns a 4 x 4 patch -- 128-bit LDS,
+//    neighbours by warp shuffle, rolling 3-row register window, and a loop-free
+//    form of the local rule in fp32 (d8_plain_cell); the four codes of a row go
+//    out as one 32-bit store.  No seeds => no taint pass.
+//  * all other tiles: the box is converted to int32 and the general
+//    per-cell rule (seeds, NULL neighbours, taint flag) runs as three passes
+//    through shared memory.
 // 4 B read + 1 B written per cell (5 B/cell algorithmic).
 #include "ht_common.cuh"
 
@@ -35,9 +42,10 @@ constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
 constexpr int DW = TW + 2, DH = TH + 2; // cells whose direction is computed
 constexpr int DX0 = 15;                 // dirs column of ring column 0: tile column 0 sits at 16
 constexpr int DP = 160;                 // pitch of the direction byte tile
-constexpr int32_t INVALID = 1 << 30;    // NULL or outside the region; valid |alt| < 2^29
-constexpr int32_t ALT_LIMIT = 1 << 29;
+constexpr int32_t INVALID = 1 << 30;    // NULL or outside the region
+constexpr int32_t ALT_LIMIT = 1 << 24;  // valid |alt| < 2^24 mm: exact as fp32
 constexpr int32_t DCLAMP = 1 << 27;     // differences are compared after clamping to +-2^27
+constexpr float F_INVALID = 3.0e38f;    // NULL / outside, while the box holds floats
 
 struct D8Args {
     int64_t rows, cols;       // owned rows, columns
@@ -48,6 +56,7 @@ struct D8Args {
     float nodata;
     double ew, ns, diag;
     float inv_ew, inv_ns, inv_diag;
+    float r_ew, r_ns;         // diag / ew, diag / ns
     uint8_t *packed;
     int64_t packed_ld;
     unsigned long long *counters; // [0] pits, [1] ties, [2] elevations out of range
@@ -61,10 +70,9 @@ __device__ __forceinline__ int ct2code(int ct) { return (0x37518426u >> (4 * ct)
 // GRASS direction code that points at window cell k = {3, 2, 1, 4, 0, 8, 5, 6, 7}
 __device__ __forceinline__ int win2code(int k) { return (int)((0x765804123ULL >> (4 * k)) & 0xF); }
 
-// rule R1: (int)(z*1000 +- 0.5) in double, as GRASS ele_round()
-__device__ __forceinline__ int32_t alt_from_f32(float z)
+// rule R1: (int)(z*1000 +- 0.5) in double, as GRASS ele_round(); d = z * 1000
+__device__ __forceinline__ int32_t alt_from_f64(double d)
 {
-    const double d = (double)z * 1000.0;
     return (int32_t)(d > 0 ? d + 0.5 : d - 0.5);
 }
 
@@ -162,6 +170,77 @@ __device__ __forceinline__ uint8_t d8_cell(int32_t w0, int32_t w1, int32_t w2, i
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// plain tiles: all nine cells valid, no seed in sight
+// ---------------------------------------------------------------------------
+// Loop-free form of rule R4 on a tie-free window.  d_k = a_k - c (negative =
+// lower).  r.watershed walks the lower neighbours in ascending order, takes a
+// cardinal at once and skips a diagonal whose slope is smaller than that of a
+// flanking cardinal which is still unworked (= higher than the diagonal).  A
+// flank lower than the diagonal wins the walk anyway, so the cell chosen is the
+// lowest of {cardinals} + {diagonals with slope >= both flanks}:
+//     diagonal usable  <=>  d_diag <= min(d_ew * diag/ew, d_ns * diag/ns).
+// Keys 8*d + ct rank the candidates (exact while |d| < 2^21); `amb` asks for the
+// exact integer / double evaluation (d8_cell) when a slope comparison is within
+// 1e-6 relative of equality or a drop is too large for the fp32 key.
+// exact evaluation of a plain window (rare: a slope comparison too close for fp32)
+__device__ __noinline__ int d8_exact_cell(float w0, float w1, float w2, float w3, float c, float w5,
+                                          float w6, float w7, float w8, double ew, double ns,
+                                          double diag, float inv_ew, float inv_ns, float inv_diag)
+{
+    D8Args p; // only the slope terms are read
+    p.ew = ew; p.ns = ns; p.diag = diag;
+    p.inv_ew = inv_ew; p.inv_ns = inv_ns; p.inv_diag = inv_diag;
+    unsigned pp = 0, tt = 0;
+    return d8_cell<false>((int)w0, (int)w1, (int)w2, (int)w3, (int)c, (int)w5, (int)w6, (int)w7,
+                          (int)w8, false, 0, p, pp, tt);
+}
+
+struct Row6f {
+    float v[6]; // columns -1 .. 4 relative to the thread's quad
+};
+
+__device__ __forceinline__ Row6f load_row6(const float *srow, int lane)
+{
+    Row6f r;
+    const float4 c = *reinterpret_cast<const float4 *>(srow + PADL + 4 * lane);
+    float l = __shfl_up_sync(0xffffffffu, c.w, 1);
+    float rt = __shfl_down_sync(0xffffffffu, c.x, 1);
+    if (lane == 0)
+        l = srow[PADL - 1];
+    if (lane == 31)
+        rt = srow[PADL + TW];
+    r.v[0] = l; r.v[1] = c.x; r.v[2] = c.y; r.v[3] = c.z; r.v[4] = c.w; r.v[5] = rt;
+    return r;
+}
+
+__device__ __forceinline__ int d8_plain_cell(float w0, float w1, float w2, float w3, float c,
+                                             float w5, float w6, float w7, float w8,
+                                             const D8Args &p, bool &amb)
+{
+    constexpr float EPS = 1e-6f, BLOCKED = 1e30f;
+    const float dS = w7 - c, dN = w1 - c, dW = w3 - c, dE = w5 - c;
+    const float dNE = w2 - c, dSW = w6 - c, dSE = w8 - c, dNW = w0 - c;
+    // flank drops scaled to the diagonal's run
+    const float sS = dS * p.r_ns, sN = dN * p.r_ns, sW = dW * p.r_ew, sE = dE * p.r_ew;
+    float t_amb = 1.0f; // <= 0 if any comparison is too close to call
+    auto diag_key = [&](float d, float s_ew, float s_ns, float ct) -> float {
+        const float m = fminf(s_ew, s_ns);
+        const float e = d - m; // > 0: a flank is steeper, the diagonal is skipped
+        t_amb = fminf(t_amb, fmaf(-EPS, fabsf(m), fabsf(e)));
+        return e > 0.0f ? BLOCKED : fmaf(d, 8.0f, ct);
+    };
+    const float k0 = fmaf(dS, 8.0f, 0.0f), k1 = fmaf(dN, 8.0f, 1.0f);
+    const float k2 = fmaf(dW, 8.0f, 2.0f), k3 = fmaf(dE, 8.0f, 3.0f);
+    const float k4 = diag_key(dNE, sE, sN, 4.0f), k5 = diag_key(dSW, sW, sS, 5.0f);
+    const float k6 = diag_key(dSE, sE, sS, 6.0f), k7 = diag_key(dNW, sW, sN, 7.0f);
+    const float kmin = fminf(fminf(fminf(k0, k1), fminf(k2, k3)), fminf(fminf(k4, k5), fminf(k6, k7)));
+    amb = t_amb <= 0.0f || kmin <= -16777208.0f;
+    const int ct = __float2int_rn(kmin) & 7;
+    return kmin < 0.0f ? ct2code(ct) : 0; // 0 = pit: not a conditioned DEM
+}
+
 template <bool VALIDATE>
 __global__ void __launch_bounds__(THREADS, 3)
 d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
@@ -218,21 +297,73 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             any_edge = 0;
         ht::mbar_wait(&full[s], (k / STAGES) & 1);
 
-        // ---- pass 0: float metres -> GRASS integer millimetres, in place
-        for (int i = tid; i < BW * BH; i += THREADS) {
-            const int yy = i / BW, xx = i - yy * BW;
-            const float z = __int_as_float(alt[i]);
-            const bool inside = yy >= ay_lo && yy <= ay_hi && xx >= ax_lo && xx <= ax_hi;
-            const bool null = !inside || (p.has_nodata && z == p.nodata) || z != z;
-            int32_t a = INVALID;
-            if (!null) {
-                a = alt_from_f32(z);
-                if (a >= ALT_LIMIT || a <= -ALT_LIMIT) {
-                    a = a > 0 ? ALT_LIMIT - 1 : -ALT_LIMIT + 1;
-                    range++;
+        // ---- pass 0: float metres -> GRASS integer millimetres (integer-valued
+        // floats), in place.  Outside the raster the TMA filled NaN.
+        bool saw_invalid = false;
+        {
+            float4 *box = reinterpret_cast<float4 *>(alt);
+            for (int i = tid; i < BW * BH / 4; i += THREADS) {
+                float4 q = box[i];
+                float *z = reinterpret_cast<float *>(&q);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool null = (p.has_nodata && z[j] == p.nodata) || z[j] != z[j];
+                    float a = F_INVALID;
+                    if (!null) {
+                        const double d = (double)z[j] * 1000.0;
+                        if (fabs(d) < 16777215.0)
+                            a = (float)alt_from_f64(d);
+                        else {
+                            a = d > 0 ? (float)(ALT_LIMIT - 1) : (float)(1 - ALT_LIMIT);
+                            range++;
+                        }
+                    }
+                    saw_invalid |= null;
+                    z[j] = a;
                 }
+                box[i] = q;
             }
-            alt[i] = a;
+        }
+        // plain tile: nothing but valid cells in the box, no raster border in the
+        // ring, and not a tile row that also stores a neighbour band's halo row
+        const bool framed = yy_top < 0 && xx_left < 0 && yy_bot >= DH && xx_right >= DW &&
+                            !(ty == 0 && p.halo_top) && !(ty == p.tiles_y - 1 && p.halo_bot) &&
+                            y0 + TH <= p.rows && x0 + TW <= p.cols;
+        const bool plain = !__syncthreads_or(saw_invalid) && framed && !VALIDATE;
+
+        if (plain) {
+            // ---- warp -> 4 rows, lane -> 4 columns, rolling 3-row window
+            const int warp = tid >> 5, lane = tid & 31;
+            const float *fb = reinterpret_cast<const float *>(alt);
+            const int yyc = 2 + 4 * warp; // box row of the first centre row
+            Row6f ra = load_row6(fb + (yyc - 1) * BW, lane);
+            Row6f rb = load_row6(fb + yyc * BW, lane);
+            uint8_t *dst = p.packed + (y0 + 4 * warp) * p.packed_ld + x0 + 4 * lane;
+#pragma unroll
+            for (int i = 0; i < 4; i++, dst += p.packed_ld) {
+                const Row6f rc = load_row6(fb + (yyc + 1 + i) * BW, lane);
+                uint32_t out = 0;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    bool amb;
+                    int code = d8_plain_cell(ra.v[c], ra.v[c + 1], ra.v[c + 2], rb.v[c], rb.v[c + 1],
+                                             rb.v[c + 2], rc.v[c], rc.v[c + 1], rc.v[c + 2], p, amb);
+                    if (amb)
+                        code = d8_exact_cell(ra.v[c], ra.v[c + 1], ra.v[c + 2], rb.v[c], rb.v[c + 1],
+                                             rb.v[c + 2], rc.v[c], rc.v[c + 1], rc.v[c + 2], p.ew, p.ns,
+                                             p.diag, p.inv_ew, p.inv_ns, p.inv_diag);
+                    out |= (uint32_t)code << (8 * c);
+                }
+                *reinterpret_cast<uint32_t *>(dst) = out;
+                ra = rb;
+                rb = rc;
+            }
+        }
+        else {
+        // ---- general tiles: int32 box, three passes through shared memory
+        for (int i = tid; i < BW * BH; i += THREADS) {
+            const float f = __int_as_float(alt[i]);
+            alt[i] = f == F_INVALID ? INVALID : (int32_t)f;
         }
         __syncthreads();
 
@@ -314,6 +445,8 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             }
         }
 
+        } // general tile
+
         ht::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -353,6 +486,7 @@ int setup(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_noda
     p.ew = ewres; p.ns = nsres; p.diag = sqrt(ewres * ewres + nsres * nsres);
     p.inv_ew = (float)(1.0 / p.ew); p.inv_ns = (float)(1.0 / p.ns);
     p.inv_diag = (float)(1.0 / p.diag);
+    p.r_ew = (float)(p.diag / p.ew); p.r_ns = (float)(p.diag / p.ns);
     p.packed = nullptr; p.packed_ld = 0; p.counters = nullptr;
     const float *base = dem - (int64_t)p.halo_top * ld;
     return ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,

@@ -46,7 +46,7 @@ def _validate(buf, ld, rows, cols, nodata, dev):
            0, 0, counts.data_ptr(), D.stream_ptr())
     c = counts.cpu()
     if int(c[2]):
-        raise ValueError(f"{int(c[2])} cells have |elevation| >= 2**29 mm; not supported")
+        raise ValueError(f"{int(c[2])} cells have |elevation| >= 2**24 mm (16 777 m); not supported")
     return int(c[0]), int(c[1])
 
 

@@ -78,7 +78,7 @@ int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_
               int64_t packed_ld, void *stream);
 /* counts3[0] = pits (non-seed cells without a strictly lower neighbour),
  * counts3[1] = cells whose 3x3 window holds two equal integer elevations,
- * counts3[2] = cells whose |elevation| >= 2^29 mm (unsupported; clamped) */
+ * counts3[2] = cells whose |elevation| >= 2^24 mm = 16 777 m (unsupported; clamped) */
 int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,
                                    int64_t ld, int has_nodata, float nodata,
                                    int64_t row0, int64_t total_rows, int halo_top,

@@ -1,0 +1,31 @@
+#!/bin/bash
+# One GPU-box pass (run under gpurun): GPU parity tests, the bench line, the ncu
+# launch list of the same bench command and one `--set full` capture of every
+# kernel of the path.  Outputs land in gpurun_out/; tools/ncu_summary.py turns
+# the reports into the committed summaries under profiles/.
+#   usage: bash tools/gpu_round.sh <tag> [notest] [noprof]
+tag=${1:-r1}
+out=gpurun_out
+mkdir -p $out
+if [[ " $* " != *" notest "* ]]; then
+  python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1
+  echo "pytest rc=$?"; tail -3 $out/pytest_$tag.log
+fi
+python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err
+echo "bench rc=$?"; cat $out/bench_$tag.json
+if [[ " $* " == *" noprof "* ]]; then exit 0; fi
+# launch list of the bench command (per-launch times are cold-cache: compare shares)
+python bench.py --steps 2 --warmup 1 > $out/plain_$tag.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file $out/launches_$tag.csv python bench.py --steps 2 --warmup 1 > $out/ncu_bench_$tag.log 2>&1
+echo "launch list rc=$?"
+# full capture: the four kernels of one D8 + accumulation step (second step: warm)
+python tools/prof_run.py 10000 2 > $out/plain2_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on \
+    -k regex:'d8_kernel|acc_local|coarse_resolve|acc_final|acc_fused' -s 4 -c 4 -f \
+    -o $out/prof_path_$tag python tools/prof_run.py 10000 2 > $out/ncu_path_$tag.log 2>&1
+echo "path capture rc=$?"
+python tools/prof_terrain.py 16384 0 > $out/plain3_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:terrain_kernel -s 2 -c 1 -f \
+    -o $out/prof_terrain_$tag python tools/prof_terrain.py 16384 0 > $out/ncu_terrain_$tag.log 2>&1
+echo "terrain capture rc=$?"
