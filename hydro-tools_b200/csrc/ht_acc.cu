@@ -412,48 +412,74 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 
 // ===========================================================================
 // Count modes (cell counts, taint counts): lean integer kernels.
-//   stage A  acc_local_cnt_kernel : receiver offsets -> scatter in-degree ->
-//            flattened chain walk with ONE shared atomic per edge (the 32-bit
-//            word carries [donors to come : 4 | link code : 4 | value : 24]); writes the
-//            tile-local count of every cell (<= 4096, u16) for stage C.
+//   stage A  acc_local_cnt_kernel : subtree sums over the tile's forest by
+//            POINTER DOUBLING in shared memory.  One 32-bit word per cell,
+//                [29] root (no receiver inside the tile) | [28] active |
+//                [27:16] cell 2^k steps downstream (active) or the root of the
+//                cell's path (done) | [15:0] sum over the 2^k cells upstream,
+//            round k: every active cell hands its sum to the cell 2^k steps
+//            downstream (one shared atomic into `delta`) and doubles its pointer;
+//            ~log2(longest path) rounds, every lane busy in every round -- a
+//            river trunk is never walked cell by cell.  The rounds leave, for
+//            every cell, its tile-local count (u16 -> stage C) and the cell its
+//            path leaves the tile through (-> boundary graph links).
 //   stage C  acc_final_cnt_kernel : final = tile-local count + inflow of every
 //            entry cell upstream; each entry's inflow is added along its path to
 //            the tile exit by an independent walker (no ordering needed).
+// Producers of the packed grid guarantee that a flowing cell (code 1..8, no
+// NEG / EDGE / NULL flag) points at a valid cell (ht_d8.cu by construction,
+// ht_dir_pack_i8 by flagging the others EDGE), so no target is re-checked here.
 // ===========================================================================
-// receiver offsets; everything >= R_EXIT is "the chain ends here"
-constexpr int16_t R_EXIT = 0x4000;  // receiver lies outside the tile
-constexpr int16_t R_NULL = 0x4001;  // NULL cell / outside the raster
-constexpr int16_t R_TERM = 0x4002;  // no receiver
-constexpr int SMC_ROFF = SM_EFF;                  // int16[T*T]
-constexpr int SMC_LO = SMC_ROFF + T * T * 2;      // uint32[T*T]
-constexpr int SMC_Q = SMC_LO + T * T * 4;         // uint16[T*T] queue of source cells
-constexpr int SMC_BAR = SMC_Q + T * T * 2;        // mbarrier, then queue head / size
+constexpr unsigned FLAGS_STOP = HT_DIR_NEG | HT_DIR_EDGE | HT_DIR_NULL;
+constexpr unsigned J_SUM = 0x0000FFFFu, J_PTR = 0x0FFF0000u, J_ACTIVE = 1u << 28, J_ROOT = 1u << 29;
+constexpr int MAX_ROUNDS = 13; // 2^13 > T*T: only a cyclic (invalid) direction grid gets here
+
+constexpr int SMC_LO = SM_EFF;                   // uint32[T*T] cell words
+constexpr int SMC_DELTA = SMC_LO + T * T * 4;    // uint32[T*T] sums handed over in a round
+constexpr int SMC_BAR = SMC_DELTA + T * T * 4;   // mbarrier, then counters
 constexpr int SMC_TOTAL = SMC_BAR + 32;
 
-struct RingBounds { int ry_lo, ry_hi, rx_lo, rx_hi; }; // usable ring-tile cells (inclusive)
-
-// offset (dr * T + dc) of GRASS code 1..8 inside the T x T tile arrays, from a
-// packed table of signed bytes: codes 1-4 = -63, -64, -65, -1; 5-8 = 63, 64, 65, 1
+// offset (dr * T + dc) of GRASS code 1..8 inside the T x T tile arrays
+__host__ __device__ constexpr int link_offset_of(int code)
+{
+    return code == 1 ? -T + 1 : code == 2 ? -T : code == 3 ? -T - 1 : code == 4 ? -1
+         : code == 5 ? T - 1 : code == 6 ? T : code == 7 ? T + 1 : code == 8 ? 1 : 0;
+}
+// the same as a packed table of signed bytes: codes 1-4 = -63, -64, -65, -1; 5-8 = 63, 64, 65, 1
 __device__ __forceinline__ int link_offset(unsigned code)
 {
     const unsigned tab = code <= 4u ? 0xFFBFC0C1u : 0x0141403Fu;
     return (int)(signed char)(tab >> (8u * ((code - 1u) & 3u)));
 }
 
-__device__ __forceinline__ RingBounds ring_bounds(const AccArgs &p, int64_t x0, int64_t y0)
+// codes that leave the tile through its west / east / north / south side (bit = code)
+constexpr unsigned EX_W = (1u << 3) | (1u << 4) | (1u << 5), EX_E = (1u << 1) | (1u << 7) | (1u << 8);
+constexpr unsigned EX_N = (1u << 1) | (1u << 2) | (1u << 3), EX_S = (1u << 5) | (1u << 6) | (1u << 7);
+
+// boundary-graph slot of the cell that (ly, lx) of tile (tx, ty) drains into
+// through `code`; the target lies outside the tile.  32-bit throughout
+// (fill_args guarantees slots < 2^31).
+__device__ __forceinline__ int32_t exit_slot(const AccArgs &p, int tx, int ty, int ly, int lx, int code)
 {
-    RingBounds b;
-    b.ry_lo = (int)max((int64_t)0, 1 - y0 - p.halo_top);
-    b.ry_hi = (int)min((int64_t)RH - 1, p.rows + p.halo_bot - y0);
-    b.rx_lo = (int)max((int64_t)XO - 1, XO - x0);
-    b.rx_hi = (int)min((int64_t)XO + T, XO + p.cols - 1 - x0);
-    return b;
+    const int lr = ty * T + ly + code_dr(code), gc = tx * T + lx + code_dc(code);
+    const int rows = (int)p.rows;
+    const int nt = p.tiles_x * p.tiles_y * SLOTS;
+    if (lr < 0)
+        return nt + gc;
+    if (lr >= rows)
+        return nt + (int)p.cols + gc;
+    const int ty2 = lr >> 6, tx2 = gc >> 6, ly2 = lr & (T - 1), lx2 = gc & (T - 1);
+    const int h2 = min(T, rows - ty2 * T);
+    const int k2 = ly2 == 0 ? lx2 : ly2 == h2 - 1 ? T + lx2 : lx2 == 0 ? 2 * T + ly2 : 3 * T + ly2;
+    return (ty2 * p.tiles_x + tx2) * SLOTS + k2;
 }
 
-__device__ __forceinline__ bool ring_valid(const uint8_t *pk, const RingBounds &rb, int yy, int xx)
+// does the (valid, flowing) perimeter cell (ly, lx) drain out of a th x tw tile?
+__device__ __forceinline__ bool leaves_tile(unsigned b, int ly, int lx, int th, int tw)
 {
-    return yy >= rb.ry_lo && yy <= rb.ry_hi && xx >= rb.rx_lo && xx <= rb.rx_hi &&
-           !(pk[yy * RP + xx] & HT_DIR_NULL);
+    const unsigned ex = (lx == 0 ? EX_W : 0u) | (lx == tw - 1 ? EX_E : 0u) |
+                        (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u);
+    return !(b & FLAGS_STOP) && ((ex >> (b & HT_DIR_CODE)) & 1u);
 }
 
 template <int WMODE>
@@ -462,209 +488,206 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *pk = smem_raw;
-    int16_t *roff = reinterpret_cast<int16_t *>(smem_raw + SMC_ROFF);
-    uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SMC_LO);
-    uint16_t *queue = reinterpret_cast<uint16_t *>(smem_raw + SMC_Q);
+    uint32_t *word = reinterpret_cast<uint32_t *>(smem_raw + SMC_LO);
+    uint32_t *delta = reinterpret_cast<uint32_t *>(smem_raw + SMC_DELTA);
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMC_BAR);
-    int *qctl = reinterpret_cast<int *>(smem_raw + SMC_BAR + 8); // [0] head, [1] size
+    int *ctl = reinterpret_cast<int *>(smem_raw + SMC_BAR + 8); // [0] entries of the tile, [1] their place in the list
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
     if (tid == 0) {
-        qctl[0] = 0;
-        qctl[1] = 0;
+        ctl[0] = 0;
         ht::mbar_init(&bar, 1);
         ht::fence_mbar_init();
         ht::mbar_expect_tx(&bar, RH * RP);
         ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
     }
+    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
+    // thread -> 4 consecutive cells of a row, 4 passes of 16 rows
+    const int q4 = 4 * (tid & 15), r0 = tid >> 4;
+    const int cbase = r0 * T + q4;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        *reinterpret_cast<uint4 *>(delta + cbase + i * 16 * T) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     ht::mbar_wait(&bar, 0);
 
-    const RingBounds rb = ring_bounds(p, x0, y0);
-    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
+    // ---- cell words: sum = own value, pointer = receiver inside the tile
+    bool mine_active = false;
+    {
+        unsigned cm[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            cm[j] = (q4 + j == 0 ? EX_W : 0u) | (q4 + j == tw - 1 ? EX_E : 0u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int ly = r0 + 16 * i;
+            const unsigned wq = *reinterpret_cast<const unsigned *>(pk + (ly + 1) * RP + XO + q4);
+            const unsigned rm = (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u);
+            unsigned wd[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned b = (wq >> (8 * j)) & 0xFFu;
+                const bool valid = !(b & HT_DIR_NULL) && ly < th && q4 + j < tw;
+                const unsigned code = b & HT_DIR_CODE;
+                const bool link = valid && !(b & FLAGS_STOP) && code >= 1u && code <= 8u &&
+                                  !(((rm | cm[j]) >> code) & 1u);
+                const unsigned val = WMODE == W_ONE ? (valid ? 1u : 0u)
+                                                    : ((valid && (b & HT_DIR_TAINT)) ? 1u : 0u);
+                const int c = cbase + i * 16 * T + j;
+                wd[j] = link ? (val | ((unsigned)(c + link_offset(code)) << 16) | J_ACTIVE)
+                             : (val | ((unsigned)c << 16) | J_ROOT);
+                mine_active |= link;
+            }
+            *reinterpret_cast<uint4 *>(word + cbase + i * 16 * T) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+    }
+    __syncthreads();
 
-    // ---- S1: receiver offset and weight of every tile cell
-    // (tiles whose ring lies wholly inside the band need no bounds tests)
-    const bool interior = rb.ry_lo == 0 && rb.ry_hi == RH - 1 && rb.rx_lo == XO - 1 &&
-                          rb.rx_hi == XO + T && th == T && tw == T;
-#pragma unroll 4
-    for (int i = 0; i < CPT; i++) {
-        const int c = tid + i * THREADS;
-        const int ly = c >> 6, lx = c & (T - 1);
-        const int yy = ly + 1, xx = lx + XO;
-        const uint8_t b = pk[yy * RP + xx];
-        const bool ok = (interior || (ly < th && lx < tw)) && !(b & HT_DIR_NULL);
-        int16_t o = ok ? R_TERM : R_NULL;
-        unsigned w = 0;
-        if (ok) {
-            w = WMODE == W_ONE ? 1u : ((b & HT_DIR_TAINT) ? 1u : 0u);
-            const int code = b & HT_DIR_CODE;
-            if (!(b & (HT_DIR_NEG | HT_DIR_EDGE)) && code >= 1 && code <= 8) {
-                const int dr = code_dr(code), dc = code_dc(code);
-                const bool tv = interior ? !(pk[(yy + dr) * RP + xx + dc] & HT_DIR_NULL)
-                                         : ring_valid(pk, rb, yy + dr, xx + dc);
-                if (tv) {
-                    const int ny = ly + dr, nx = lx + dc;
-                    if (ny >= 0 && ny < th && nx >= 0 && nx < tw) {
-                        o = (int16_t)(dr * T + dc);
-                        w |= (unsigned)code << 24; // the word carries its own link
+    // ---- pointer doubling
+    for (int round = 0; round < MAX_ROUNDS; round++) {
+        unsigned np[16]; // pointer / state bits of my cells after this round
+        if (mine_active) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint4 w4 = *reinterpret_cast<const uint4 *>(word + cbase + i * 16 * T);
+                const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    unsigned n = w[j] & ~J_SUM;
+                    if (w[j] & J_ACTIVE) {
+                        const unsigned t = (w[j] >> 16) & 0xFFFu;
+                        const unsigned wt = word[t];
+                        const unsigned a = w[j] & J_SUM;
+                        if (a)
+                            atomicAdd(&delta[t], a);
+                        // t still active: its pointer is 2^(k+1) steps from me; else I am
+                        // done and remember the root of the path
+                        n = (wt & J_ROOT) ? (t << 16) : (wt & (J_PTR | J_ACTIVE));
                     }
-                    else
-                        o = R_EXIT;
+                    np[4 * i + j] = n;
                 }
             }
         }
-        roff[c] = o;
-        lo32[c] = w;
-    }
-    __syncthreads();
-
-    // ---- S2: in-degree by scatter (count field of the receiver's word)
-#pragma unroll 4
-    for (int i = 0; i < CPT; i++) {
-        const int c = tid + i * THREADS;
-        const int16_t o = roff[c];
-        if (o < R_EXIT)
-            atomicAdd(&lo32[c + o], 1u << 28);
-    }
-    __syncthreads();
-    // sources (no donor inside the tile) go to a queue shared by the whole CTA
-    {
-        unsigned src_mask = 0;
-#pragma unroll 4
-        for (int i = 0; i < CPT; i++) {
-            const int c = tid + i * THREADS;
-            src_mask |= ((lo32[c] >> 28) == 0u && roff[c] != R_NULL ? 1u : 0u) << i;
-        }
-        int pos = src_mask ? atomicAdd(&qctl[1], __popc(src_mask)) : 0;
-        while (src_mask) {
-            const int i = __ffs(src_mask) - 1;
-            src_mask &= src_mask - 1;
-            queue[pos++] = (uint16_t)(tid + i * THREADS);
-        }
-    }
-    __syncthreads();
-
-    // ---- S3: topological propagation.  A lane follows a chain for as long as it is
-    // the last donor to arrive, then takes the next source from the queue, so the
-    // lanes of a warp stay busy until only the longest trunks are left.
-    {
-        const int qn = qctl[1];
-        int cur = -1;
-        unsigned v = 0, word = 0;
-        for (;;) {
-            if (cur < 0) {
-                const int qi = atomicAdd(&qctl[0], 1);
-                if (qi >= qn)
-                    break;
-                cur = queue[qi];
-                word = lo32[cur];
-                v = word & 0x00FFFFFFu;
-            }
-            // the receiver's word (returned by the atomic) names the next link, so a
-            // step is one shared-memory round trip
-            const unsigned code = (word >> 24) & 0xFu;
-            if (!code) { // chain ends in this tile (exits are flushed below)
-                cur = -1;
+        __syncthreads();
+        bool still = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 d4 = *reinterpret_cast<const uint4 *>(delta + cbase + i * 16 * T);
+            if (!mine_active && !(d4.x | d4.y | d4.z | d4.w))
                 continue;
+            uint4 w4 = *reinterpret_cast<const uint4 *>(word + cbase + i * 16 * T);
+            if (mine_active) {
+                w4.x = np[4 * i + 0] | (w4.x & J_SUM);
+                w4.y = np[4 * i + 1] | (w4.y & J_SUM);
+                w4.z = np[4 * i + 2] | (w4.z & J_SUM);
+                w4.w = np[4 * i + 3] | (w4.w & J_SUM);
+                still |= ((w4.x | w4.y | w4.z | w4.w) & J_ACTIVE) != 0;
             }
-            const int rc = cur + link_offset(code);
-            const unsigned old = atomicAdd(&lo32[rc], v + 0xF0000000u);
-            if ((old >> 28) != 1u) {
-                cur = -1; // other donors still to come; the last one continues
-                continue;
-            }
-            v += old & 0x00FFFFFFu;
-            word = old;
-            cur = rc;
+            w4.x += d4.x; w4.y += d4.y; w4.z += d4.z; w4.w += d4.w;
+            *reinterpret_cast<uint4 *>(word + cbase + i * 16 * T) = w4;
+            if (d4.x | d4.y | d4.z | d4.w)
+                *reinterpret_cast<uint4 *>(delta + cbase + i * 16 * T) = make_uint4(0u, 0u, 0u, 0u);
         }
-    }
-    __syncthreads();
-
-    // ---- S3b: flow that leaves the tile feeds the boundary graph
-#pragma unroll 4
-    for (int i = 0; i < CPT; i++) {
-        const int c = tid + i * THREADS;
-        if (roff[c] != R_EXIT)
-            continue;
-        const int ly = c >> 6, lx = c & (T - 1);
-        const int code = pk[(ly + 1) * RP + lx + XO] & HT_DIR_CODE;
-        const int64_t lr = y0 + ly + code_dr(code), gc = x0 + lx + code_dc(code);
-        const int64_t s = lr < 0 ? vslot_of(p, false, gc)
-                        : lr >= p.rows ? vslot_of(p, true, gc)
-                                       : slot_of(p, lr, gc);
-        atomicAdd(reinterpret_cast<unsigned long long *>(p.base) + s,
-                  (unsigned long long)(lo32[c] & 0x00FFFFFFu));
+        mine_active = still;
+        if (!__syncthreads_or(still))
+            break;
     }
 
-    // ---- S4a: where does the path of each entry cell leave the tile?
+    // ---- boundary graph.  thread -> one perimeter slot
     {
-        const int k = tid; // one perimeter slot per thread
-        int ly, lx;
+        int ly = 0, lx = 0;
+        const bool per = perimeter_cell(tid, th, tw, ly, lx);
+        const unsigned b = per ? pk[(ly + 1) * RP + lx + XO] : (unsigned)HT_DIR_NULL;
+        // flow that leaves the tile through this cell
+        if (per && leaves_tile(b, ly, lx, th, tw)) {
+            const unsigned val = word[ly * T + lx] & J_SUM;
+            if (val)
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.base) +
+                              exit_slot(p, tx, ty, ly, lx, (int)(b & HT_DIR_CODE)),
+                          (unsigned long long)val);
+        }
+        // entry cell: a cell outside the tile drains into it
         bool entry = false;
-        int32_t nxt = TERMINAL;
-        int64_t slot = 0;
-        if (perimeter_cell(k, th, tw, ly, lx) && !(pk[(ly + 1) * RP + lx + XO] & HT_DIR_NULL)) {
+        if (per && !(b & HT_DIR_NULL)) {
             const int yy = ly + 1, xx = lx + XO;
 #pragma unroll
             for (int kk = 0; kk < 9; kk++) {
                 if (kk == 4)
                     continue;
                 const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
-                const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
-                if (in_tile || !ring_valid(pk, rb, ny, nx))
-                    continue;
-                const uint8_t u = pk[ny * RP + nx];
-                entry |= !(u & (HT_DIR_NEG | HT_DIR_EDGE)) && (u & HT_DIR_CODE) == win2code(8 - kk);
-            }
-            if (entry) {
-                slot = slot_of(p, y0 + ly, x0 + lx);
-                int cur = ly * T + lx;
-                int16_t o;
-                while ((o = roff[cur]) < R_EXIT)
-                    cur += o;
-                if (o == R_EXIT) {
-                    const int code = pk[((cur >> 6) + 1) * RP + (cur & (T - 1)) + XO] & HT_DIR_CODE;
-                    const int64_t lr = y0 + (cur >> 6) + code_dr(code), gc = x0 + (cur & (T - 1)) + code_dc(code);
-                    nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
-                                  : lr >= p.rows ? vslot_of(p, true, gc)
-                                                 : slot_of(p, lr, gc));
-                }
+                if (ny >= 1 && ny <= th && nx >= XO && nx < XO + tw)
+                    continue; // inside the tile
+                const unsigned u = pk[ny * RP + nx]; // outside the raster: TMA filled 0
+                entry |= !(u & FLAGS_STOP) && (u & HT_DIR_CODE) == (unsigned)win2code(8 - kk);
             }
         }
-        publish_entry(p, entry, slot, nxt);
+        const unsigned m = __ballot_sync(0xffffffffu, entry);
+        int at = 0;
+        if (lane == 0 && m)
+            at = atomicAdd(&ctl[0], __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+        __syncthreads();
+        if (tid == 0 && ctl[0])
+            ctl[1] = atomicAdd(p.nlist, ctl[0]);
+        __syncthreads();
+        if (entry) {
+            // where the path that enters here leaves the tile: the root of the cell
+            const unsigned w = word[ly * T + lx];
+            const int rc = (int)((w >> 16) & 0xFFFu), cy = rc >> 6, cx = rc & (T - 1);
+            const unsigned rb = pk[(cy + 1) * RP + cx + XO];
+            const int32_t slot = tile * SLOTS + tid;
+            p.list[ctl[1] + at] = slot;
+            p.next[slot] = leaves_tile(rb, cy, cx, th, tw)
+                               ? exit_slot(p, tx, ty, cy, cx, (int)(rb & HT_DIR_CODE))
+                               : TERMINAL;
+        }
     }
 
-    // ---- S4b: tile-local counts for stage C (thread -> one column, every 4th row)
+    // ---- tile-local counts for stage C (u16, 8-byte stores)
     {
-        const int lx = tid & (T - 1), ly0 = tid >> 6;
-        uint16_t *dst = p.lacc + (y0 + ly0) * p.lacc_ld + x0 + lx;
-        const int64_t step = 4 * p.lacc_ld;
-        if (lx < tw) {
-#pragma unroll 4
-            for (int i = 0; i < CPT; i++, dst += step)
-                if (ly0 + 4 * i < th)
-                    *dst = (uint16_t)lo32[tid + i * THREADS];
+        uint16_t *dst = p.lacc + (y0 + r0) * p.lacc_ld + x0 + q4;
+        const int64_t step = 16 * p.lacc_ld;
+#pragma unroll
+        for (int i = 0; i < 4; i++, dst += step) {
+            if (r0 + 16 * i >= th || q4 >= tw)
+                continue;
+            const uint4 w4 = *reinterpret_cast<const uint4 *>(word + cbase + i * 16 * T);
+            const unsigned a = (w4.x & J_SUM) | (w4.y << 16), b = (w4.z & J_SUM) | (w4.w << 16);
+            if (q4 + 3 < tw)
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(a, b);
+            else {
+                const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+                for (int j = 0; j < 4 && q4 + j < tw; j++)
+                    dst[j] = (uint16_t)w[j];
+            }
         }
     }
 }
 
+
+// stage C cell words: lo32 = [31:24] signed receiver offset inside the tile (0 =
+// none) | [23:0] low part of the count; hi32 = count >> 16.  A walker adds its
+// inflow split 16 / rest, so the low field never carries into the offset
+// (<= 256 walkers x 65535 + 4096 < 2^24), and the atomic that adds the low part
+// returns the link to follow.
 constexpr int SMF_LO = T * T;               // after the 64x64 packed tile
 constexpr int SMF_HI = SMF_LO + T * T * 4;
-constexpr int SMF_BAR = SMF_HI + T * T * 4;
+constexpr int SMF_LUT = SMF_HI + T * T * 4; // uint32[16] code -> offset field
+constexpr int SMF_BAR = SMF_LUT + 64;
 constexpr int SMF_TOTAL = SMF_BAR + 16;
 
 template <int WMODE>
-__global__ void __launch_bounds__(THREADS, 6)
+__global__ void __launch_bounds__(THREADS, 5)
 acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *pk = smem_raw; // 64 x 64, no ring
-    uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SMF_LO); // value = hi * 2^20 + lo
+    uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SMF_LO);
     uint32_t *hi32 = reinterpret_cast<uint32_t *>(smem_raw + SMF_HI);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMF_LUT);
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMF_BAR);
 
     const int tid = threadIdx.x;
@@ -677,96 +700,151 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         ht::mbar_expect_tx(&bar, T * T);
         ht::tma_load_2d(pk, &map, (int)x0, (int)y0 + p.halo_top, &bar);
     }
+    if (tid < 16)
+        lut[tid] = ((unsigned)link_offset_of(tid) & 0xFFu) << 24;
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
-    // tile-local counts while the TMA is in flight (thread -> one column, every 4th row)
-    const int mx = tid & (T - 1), my0 = tid >> 6;
+    // thread -> 4 consecutive cells of a row, 4 passes of 16 rows (as in stage A)
+    const int q4 = 4 * (tid & 15), r0 = tid >> 4;
+    const int cbase = r0 * T + q4;
+    const bool wide = q4 + 3 < tw;
+
+    // tile-local counts and this tile's resolved inflow while the TMA is in flight
+    uint2 lc[4];
     {
-        const uint16_t *src = p.lacc + (y0 + my0) * p.lacc_ld + x0 + mx;
-        const int64_t step = 4 * p.lacc_ld;
-#pragma unroll 4
-        for (int i = 0; i < CPT; i++, src += step) {
-            lo32[tid + i * THREADS] = (mx < tw && my0 + 4 * i < th) ? (unsigned)*src : 0u;
-            hi32[tid + i * THREADS] = 0u;
+        const uint16_t *src = p.lacc + (y0 + r0) * p.lacc_ld + x0 + q4;
+        const int64_t step = 16 * p.lacc_ld;
+#pragma unroll
+        for (int i = 0; i < 4; i++, src += step) {
+            lc[i] = make_uint2(0u, 0u);
+            if (r0 + 16 * i >= th || q4 >= tw)
+                continue;
+            if (wide)
+                lc[i] = *reinterpret_cast<const uint2 *>(src);
+            else {
+                unsigned h[4] = {0u, 0u, 0u, 0u};
+                for (int j = 0; j < 4 && q4 + j < tw; j++)
+                    h[j] = src[j];
+                lc[i] = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+            }
         }
     }
+    int ely = 0, elx = 0;
+    unsigned long long inflow = 0;
+    if (perimeter_cell(tid, th, tw, ely, elx))
+        inflow = reinterpret_cast<const unsigned long long *>(p.inflow)[(int64_t)tile * SLOTS + tid];
     __syncthreads();
     ht::mbar_wait(&bar, 0);
 
-    // ---- walkers: one per entry cell with inflow
-    for (int k = tid; k < SLOTS; k += THREADS) {
-        int ly, lx;
-        if (!perimeter_cell(k, th, tw, ly, lx))
-            continue;
-        const unsigned long long inflow =
-            reinterpret_cast<const unsigned long long *>(p.inflow)[slot_of(p, y0 + ly, x0 + lx)];
-        if (!inflow)
-            continue;
-        const unsigned i_lo = (unsigned)(inflow & 0xFFFFFu), i_hi = (unsigned)(inflow >> 20);
-        int cy = ly, cx = lx;
-        for (;;) {
-            const int cur = cy * T + cx;
-            if (i_lo)
-                atomicAdd(&lo32[cur], i_lo);
-            if (i_hi)
-                atomicAdd(&hi32[cur], i_hi);
-            const uint8_t b = pk[cur];
-            const int code = b & HT_DIR_CODE;
-            if ((b & (HT_DIR_NEG | HT_DIR_EDGE)) || code < 1 || code > 8)
-                break;
-            cy += code_dr(code);
-            cx += code_dc(code);
-            if (cy < 0 || cy >= th || cx < 0 || cx >= tw || (pk[cy * T + cx] & HT_DIR_NULL))
-                break;
+    // ---- cell words
+    {
+        unsigned cm[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            cm[j] = (q4 + j == 0 ? EX_W : 0u) | (q4 + j == tw - 1 ? EX_E : 0u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int ly = r0 + 16 * i;
+            const unsigned wq = *reinterpret_cast<const unsigned *>(pk + ly * T + q4);
+            const unsigned rm = (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u);
+            const unsigned cnt[4] = {lc[i].x & 0xFFFFu, lc[i].x >> 16, lc[i].y & 0xFFFFu, lc[i].y >> 16};
+            unsigned wd[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned b = (wq >> (8 * j)) & 0xFFu;
+                const unsigned code = b & HT_DIR_CODE;
+                const bool link = !(b & FLAGS_STOP) && ly < th && q4 + j < tw &&
+                                  !(((rm | cm[j]) >> code) & 1u);
+                wd[j] = (link ? lut[code] : 0u) | cnt[j];
+            }
+            *reinterpret_cast<uint4 *>(lo32 + cbase + i * 16 * T) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            *reinterpret_cast<uint4 *>(hi32 + cbase + i * 16 * T) = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     __syncthreads();
 
-    // ---- outputs
-    if (mx >= tw)
-        return;
-    double *accp = p.acc ? p.acc + (y0 + my0) * p.acc_ld + x0 + mx : nullptr;
-    int8_t *dirp = (WMODE == W_ONE && p.dir_out) ? p.dir_out + (y0 + my0) * p.dir_ld + x0 + mx : nullptr;
-#pragma unroll 2
-    for (int i = 0; i < CPT; i++) {
-        const int c = tid + i * THREADS;
-        const int ly = my0 + 4 * i, lx = mx;
-        if (ly >= th)
-            break;
-        const uint8_t b = pk[c];
-        const bool null = b & HT_DIR_NULL;
-        const unsigned long long cnt = ((unsigned long long)hi32[c] << 20) + lo32[c];
-        const double a = (double)cnt;
-        if (accp)
-            accp[(int64_t)(4 * i) * p.acc_ld] = null ? __longlong_as_double(0x7ff8000000000000LL) : a;
-        if (dirp) {
-            const int code = b & HT_DIR_CODE;
-            int out;
-            if (null)
-                out = -128;
-            else if (b & HT_DIR_NEG)
-                out = -code;
-            else if ((b & HT_DIR_EDGE) && cnt >= 60ull) {
-                // rule R5: an edge cell that is a swale (|acc| >= 60) gets its outward
-                // code back: first neighbour outside the raster / NULL in the order
-                // S,N,W,E,NE,SW,SE,NW (rare: read the neighbours from global memory)
-                out = 0;
+    // ---- walkers: one per entry cell with inflow
+    if (inflow) {
+        const unsigned i_lo = (unsigned)(inflow & 0xFFFFu), i_hi = (unsigned)(inflow >> 16);
+        int cur = ely * T + elx;
+        for (;;) {
+            const unsigned old = atomicAdd(&lo32[cur], i_lo);
+            if (i_hi)
+                atomicAdd(&hi32[cur], i_hi);
+            const int off = (int)old >> 24;
+            if (off == 0)
+                break;
+            cur += off;
+        }
+    }
+    __syncthreads();
+
+    // ---- outputs: 4 cells per thread and pass
+    double *accp = p.acc ? p.acc + (y0 + r0) * p.acc_ld + x0 + q4 : nullptr;
+    int8_t *dirp = (WMODE == W_ONE && p.dir_out) ? p.dir_out + (y0 + r0) * p.dir_ld + x0 + q4 : nullptr;
 #pragma unroll
-                for (int ct = 7; ct >= 0; ct--) {
-                    const int kk = ct2win(ct);
-                    const int64_t lr = y0 + ly + kk / 3 - 1, gc = x0 + lx + kk % 3 - 1;
-                    const int64_t gr = p.row0 + lr;
-                    bool outside = gr < 0 || gr >= p.total_rows || gc < 0 || gc >= p.cols;
-                    if (!outside)
-                        outside = p.packed[lr * p.packed_ld + gc] & HT_DIR_NULL;
-                    if (outside)
-                        out = -win2code(kk);
+    for (int i = 0; i < 4; i++) {
+        const int ly = r0 + 16 * i;
+        if (ly >= th || q4 >= tw)
+            break;
+        const uint4 l4 = *reinterpret_cast<const uint4 *>(lo32 + cbase + i * 16 * T);
+        const uint4 h4 = *reinterpret_cast<const uint4 *>(hi32 + cbase + i * 16 * T);
+        const unsigned wq = *reinterpret_cast<const unsigned *>(pk + ly * T + q4);
+        const unsigned lo[4] = {l4.x, l4.y, l4.z, l4.w}, hi[4] = {h4.x, h4.y, h4.z, h4.w};
+        double a[4];
+        unsigned dout = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned b = (wq >> (8 * j)) & 0xFFu;
+            const bool null = b & HT_DIR_NULL;
+            const unsigned long long cnt = ((unsigned long long)hi[j] << 16) + (lo[j] & 0x00FFFFFFu);
+            a[j] = null ? __longlong_as_double(0x7ff8000000000000LL) : (double)cnt;
+            if (dirp) {
+                const int code = b & HT_DIR_CODE;
+                int out;
+                if (null)
+                    out = -128;
+                else if (b & HT_DIR_NEG)
+                    out = -code;
+                else if ((b & HT_DIR_EDGE) && cnt >= 60ull) {
+                    // rule R5: an edge cell that is a swale (|acc| >= 60) gets its outward
+                    // code back: first neighbour outside the raster / NULL in the order
+                    // S,N,W,E,NE,SW,SE,NW (rare: read the neighbours from global memory)
+                    out = 0;
+#pragma unroll
+                    for (int ct = 7; ct >= 0; ct--) {
+                        const int kk = ct2win(ct);
+                        const int64_t lr = y0 + ly + kk / 3 - 1, gc = x0 + q4 + j + kk % 3 - 1;
+                        const int64_t gr = p.row0 + lr;
+                        bool outside = gr < 0 || gr >= p.total_rows || gc < 0 || gc >= p.cols;
+                        if (!outside)
+                            outside = p.packed[lr * p.packed_ld + gc] & HT_DIR_NULL;
+                        if (outside)
+                            out = -win2code(kk);
+                    }
+                    if (out == 0)
+                        out = code; // not an edge after all (foreign packed grid)
                 }
-                if (out == 0)
-                    out = code; // not an edge after all (foreign packed grid)
+                else
+                    out = code;
+                dout |= ((unsigned)out & 0xFFu) << (8 * j);
             }
-            else
-                out = code;
-            dirp[(int64_t)(4 * i) * p.dir_ld] = (int8_t)out;
+        }
+        if (wide) {
+            if (accp) {
+                double2 *d2 = reinterpret_cast<double2 *>(accp + (int64_t)(16 * i) * p.acc_ld);
+                d2[0] = make_double2(a[0], a[1]);
+                d2[1] = make_double2(a[2], a[3]);
+            }
+            if (dirp)
+                *reinterpret_cast<unsigned *>(dirp + (int64_t)(16 * i) * p.dir_ld) = dout;
+        }
+        else {
+            for (int j = 0; j < 4 && q4 + j < tw; j++) {
+                if (accp)
+                    accp[(int64_t)(16 * i) * p.acc_ld + j] = a[j];
+                if (dirp)
+                    dirp[(int64_t)(16 * i) * p.dir_ld + j] = (int8_t)(dout >> (8 * j));
+            }
         }
     }
 }
@@ -1181,6 +1259,10 @@ extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t ro
     if (!packed || packed_ld < cols || (mode == W_F32 && (!w || w_ld < cols)) || mode < 0 ||
         mode > 2 || (acc && acc_ld < cols) || (dir_out && dir_ld < cols))
         return HT_ERR_ARG;
+    // count modes store 2 doubles / 4 direction bytes at a time
+    if (mode != W_F32 && ((acc && (((uintptr_t)acc & 15) || (acc_ld & 1))) ||
+                          (dir_out && (((uintptr_t)dir_out & 3) || (dir_ld & 3)))))
+        return HT_ERR_ALIGN;
     Workspace wk;
     if ((rc = carve(ws, ws_bytes, rows, cols, wk)))
         return rc;

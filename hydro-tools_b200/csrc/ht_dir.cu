@@ -18,8 +18,15 @@ __global__ void pack_i8_kernel(const int8_t *dir, int64_t ld, int64_t rows, int6
         uint8_t b;
         if (d == -128)
             b = HT_DIR_NULL;
-        else if (d >= 1 && d <= 8)
-            b = (uint8_t)d;
+        else if (d >= 1 && d <= 8) {
+            // a receiver outside the raster or NULL ends the path: the cell "does not
+            // pass flow on" (the accumulation kernels then never re-check a target)
+            const int64_t rr = r + (int)((0x1A900u >> (2 * d)) & 3u) - 1;
+            const int64_t cc = c + (int)((0x29018u >> (2 * d)) & 3u) - 1;
+            const bool gone = rr < 0 || rr >= rows || cc < 0 || cc >= cols ||
+                              dir[rr * ld + cc] == -128;
+            b = (uint8_t)d | (gone ? HT_DIR_EDGE : 0);
+        }
         else if (d <= -1 && d >= -8)
             b = (uint8_t)(-d) | HT_DIR_NEG;
         else

@@ -87,7 +87,9 @@ int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,
 
 /* GRASS int8 codes (-128 = NULL) <-> packed byte; used for direction rasters that
  * come from disk (FlowAccumulation(direction),
- * /root/reference/src/hydrotools/watershed.py:329-339) */
+ * /root/reference/src/hydrotools/watershed.py:329-339).  A code 1..8 whose
+ * receiver is NULL or outside the raster is flagged HT_DIR_EDGE (does not pass
+ * flow on), which is what r.flowaccumulation does with it. */
 int ht_dir_pack_i8(const int8_t *dir, int64_t ld, int64_t rows, int64_t cols,
                    uint8_t *packed, int64_t packed_ld, void *stream);
 int ht_dir_unpack_i8(const uint8_t *packed, int64_t packed_ld, int64_t rows,
@@ -102,6 +104,8 @@ int ht_dir_unpack_i8(const uint8_t *packed, int64_t packed_ld, int64_t rows,
  * stage B (ht_acc_resolve) resolves it by pointer doubling until no pointer
  * changes, stage C (ht_acc_final) writes acc (fp64; NaN where NULL) and, if
  * dir_out != NULL, the final GRASS direction codes (int8, -128 = NULL).
+ * Count modes: acc 16-B aligned with acc_ld % 2 == 0, dir_out 4-B aligned with
+ * dir_ld % 4 == 0 (HT_ERR_ALIGN otherwise).
  * ht_acc_f64 = A + B + C for an unsharded raster. */
 size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols);
 /* byte offsets of the boundary-graph arrays inside the workspace (row-band host

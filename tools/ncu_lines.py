@@ -3,6 +3,7 @@ usage: ncu_lines.py <report.ncu-rep> <kernel regex> <object.o> <mangled-name sub
 import csv, re, subprocess, sys, tempfile, os, collections
 rep, kre, obj, fn = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 35
+by_samples = len(sys.argv) > 6 and sys.argv[6] == "samples"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -39,7 +40,7 @@ for a, (n, s, thr, txt) in inst.items():
 tot = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 print(f"total warp-inst {tot}  samples {ts}")
 src = {}
-for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
     if f not in src:
         try: src[f] = open(os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "csrc", f)).read().splitlines()
         except Exception: src[f] = []
