@@ -414,9 +414,10 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // Count modes (cell counts, taint counts): lean integer kernels.
 //   stage A  acc_local_cnt_kernel : subtree sums over the tile's forest by
 //            POINTER DOUBLING in shared memory.  One 32-bit word per cell,
-//                [29] root (no receiver inside the tile) | [28] active |
-//                [27:16] cell 2^k steps downstream (active) or the root of the
-//                cell's path (done) | [15:0] sum over the 2^k cells upstream,
+//                [31:16] sum over the 2^k cells upstream | [13:2] the cell 2^k steps
+//                downstream (active) or the root of the cell's path (done; a root
+//                points at itself) -- with the two flag bits masked off this is the
+//                byte offset of that cell's word | [1] root | [0] active,
 //            round k: every active cell hands its sum to the cell 2^k steps
 //            downstream (one shared atomic into `delta`) and doubles its pointer;
 //            ~log2(longest path) rounds, every lane busy in every round -- a
@@ -431,12 +432,13 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // ht_dir_pack_i8 by flagging the others EDGE), so no target is re-checked here.
 // ===========================================================================
 constexpr unsigned FLAGS_STOP = HT_DIR_NEG | HT_DIR_EDGE | HT_DIR_NULL;
-constexpr unsigned J_SUM = 0x0000FFFFu, J_PTR = 0x0FFF0000u, J_ACTIVE = 1u << 28, J_ROOT = 1u << 29;
+constexpr unsigned J_SUM = 0xFFFF0000u, J_PTR = 0x00003FFCu, J_ACTIVE = 1u, J_ROOT = 2u;
 constexpr int MAX_ROUNDS = 13; // 2^13 > T*T: only a cyclic (invalid) direction grid gets here
 
 constexpr int SMC_LO = SM_EFF;                   // uint32[T*T] cell words
 constexpr int SMC_DELTA = SMC_LO + T * T * 4;    // uint32[T*T] sums handed over in a round
-constexpr int SMC_BAR = SMC_DELTA + T * T * 4;   // mbarrier, then counters
+constexpr int SMC_LUT = SMC_DELTA + T * T * 4;   // uint32[16] code -> pointer step | active
+constexpr int SMC_BAR = SMC_LUT + 64;            // mbarrier, then counters
 constexpr int SMC_TOTAL = SMC_BAR + 32;
 
 // offset (dr * T + dc) of GRASS code 1..8 inside the T x T tile arrays
@@ -490,6 +492,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     uint8_t *pk = smem_raw;
     uint32_t *word = reinterpret_cast<uint32_t *>(smem_raw + SMC_LO);
     uint32_t *delta = reinterpret_cast<uint32_t *>(smem_raw + SMC_DELTA);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMC_LUT);
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMC_BAR);
     int *ctl = reinterpret_cast<int *>(smem_raw + SMC_BAR + 8); // [0] entries of the tile, [1] their place in the list
 
@@ -504,6 +507,8 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         ht::mbar_expect_tx(&bar, RH * RP);
         ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
     }
+    if (tid < 16) // added to a cell's own byte offset; codes 0, 9..15 make a root
+        lut[tid] = link_offset_of(tid) ? (unsigned)(link_offset_of(tid) * 4) + J_ACTIVE : J_ROOT;
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
     // thread -> 4 consecutive cells of a row, 4 passes of 16 rows
     const int q4 = 4 * (tid & 15), r0 = tid >> 4;
@@ -517,29 +522,30 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     // ---- cell words: sum = own value, pointer = receiver inside the tile
     bool mine_active = false;
     {
-        unsigned cm[4];
+        unsigned cm[4]; // codes that do not link from column q4 + j; bit 15: outside the raster
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            cm[j] = (q4 + j == 0 ? EX_W : 0u) | (q4 + j == tw - 1 ? EX_E : 0u);
+            cm[j] = (q4 + j == 0 ? EX_W : 0u) | (q4 + j == tw - 1 ? EX_E : 0u) |
+                    (q4 + j >= tw ? 0xFFFFu : 0u) | 1u; // bit 0: code 0 never links
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int ly = r0 + 16 * i;
             const unsigned wq = *reinterpret_cast<const unsigned *>(pk + (ly + 1) * RP + XO + q4);
-            const unsigned rm = (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u);
+            const unsigned rm = (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u) | (ly >= th ? 0xFFFFu : 0u);
+            const unsigned self = (unsigned)(cbase + i * 16 * T) * 4u; // byte offset of cell j = 0
             unsigned wd[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const unsigned b = (wq >> (8 * j)) & 0xFFu;
-                const bool valid = !(b & HT_DIR_NULL) && ly < th && q4 + j < tw;
                 const unsigned code = b & HT_DIR_CODE;
-                const bool link = valid && !(b & FLAGS_STOP) && code >= 1u && code <= 8u &&
-                                  !(((rm | cm[j]) >> code) & 1u);
+                const unsigned ex = rm | cm[j];
+                // no link: a stop flag, or the receiver is outside the tile / the raster
+                const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
+                const bool valid = !(b & HT_DIR_NULL) && !(ex >> 15);
                 const unsigned val = WMODE == W_ONE ? (valid ? 1u : 0u)
                                                     : ((valid && (b & HT_DIR_TAINT)) ? 1u : 0u);
-                const int c = cbase + i * 16 * T + j;
-                wd[j] = link ? (val | ((unsigned)(c + link_offset(code)) << 16) | J_ACTIVE)
-                             : (val | ((unsigned)c << 16) | J_ROOT);
-                mine_active |= link;
+                wd[j] = self + 4u * j + (stop ? J_ROOT : lut[code]) + (val << 16);
+                mine_active |= !stop;
             }
             *reinterpret_cast<uint4 *>(word + cbase + i * 16 * T) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         }
@@ -548,7 +554,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 
     // ---- pointer doubling
     for (int round = 0; round < MAX_ROUNDS; round++) {
-        unsigned np[16]; // pointer / state bits of my cells after this round
+        unsigned np[16]; // low half (pointer, flags) of my cells after this round
         if (mine_active) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -558,14 +564,15 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                 for (int j = 0; j < 4; j++) {
                     unsigned n = w[j] & ~J_SUM;
                     if (w[j] & J_ACTIVE) {
-                        const unsigned t = (w[j] >> 16) & 0xFFFu;
-                        const unsigned wt = word[t];
-                        const unsigned a = w[j] & J_SUM;
-                        if (a)
-                            atomicAdd(&delta[t], a);
-                        // t still active: its pointer is 2^(k+1) steps from me; else I am
-                        // done and remember the root of the path
-                        n = (wt & J_ROOT) ? (t << 16) : (wt & (J_PTR | J_ACTIVE));
+                        const unsigned t = w[j] & J_PTR; // byte offset of the cell 2^k steps on
+                        const unsigned wt = *reinterpret_cast<const uint32_t *>(
+                            reinterpret_cast<const unsigned char *>(word) + t);
+                        const unsigned a = w[j] >> 16;
+                        if (WMODE == W_ONE || a)
+                            atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(delta) + t), a);
+                        // t still active: its pointer is 2^(k+1) steps from me; else I am done
+                        // and keep the root of the path (t's pointer; a root points at itself)
+                        n = wt & (J_PTR | J_ACTIVE);
                     }
                     np[4 * i + j] = n;
                 }
@@ -586,7 +593,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                 w4.w = np[4 * i + 3] | (w4.w & J_SUM);
                 still |= ((w4.x | w4.y | w4.z | w4.w) & J_ACTIVE) != 0;
             }
-            w4.x += d4.x; w4.y += d4.y; w4.z += d4.z; w4.w += d4.w;
+            w4.x += d4.x << 16; w4.y += d4.y << 16; w4.z += d4.z << 16; w4.w += d4.w << 16;
             *reinterpret_cast<uint4 *>(word + cbase + i * 16 * T) = w4;
             if (d4.x | d4.y | d4.z | d4.w)
                 *reinterpret_cast<uint4 *>(delta + cbase + i * 16 * T) = make_uint4(0u, 0u, 0u, 0u);
@@ -603,7 +610,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         const unsigned b = per ? pk[(ly + 1) * RP + lx + XO] : (unsigned)HT_DIR_NULL;
         // flow that leaves the tile through this cell
         if (per && leaves_tile(b, ly, lx, th, tw)) {
-            const unsigned val = word[ly * T + lx] & J_SUM;
+            const unsigned val = word[ly * T + lx] >> 16;
             if (val)
                 atomicAdd(reinterpret_cast<unsigned long long *>(p.base) +
                               exit_slot(p, tx, ty, ly, lx, (int)(b & HT_DIR_CODE)),
@@ -636,7 +643,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         if (entry) {
             // where the path that enters here leaves the tile: the root of the cell
             const unsigned w = word[ly * T + lx];
-            const int rc = (int)((w >> 16) & 0xFFFu), cy = rc >> 6, cx = rc & (T - 1);
+            const int rc = (int)((w & J_PTR) >> 2), cy = rc >> 6, cx = rc & (T - 1);
             const unsigned rb = pk[(cy + 1) * RP + cx + XO];
             const int32_t slot = tile * SLOTS + tid;
             p.list[ctl[1] + at] = slot;
@@ -655,13 +662,13 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             if (r0 + 16 * i >= th || q4 >= tw)
                 continue;
             const uint4 w4 = *reinterpret_cast<const uint4 *>(word + cbase + i * 16 * T);
-            const unsigned a = (w4.x & J_SUM) | (w4.y << 16), b = (w4.z & J_SUM) | (w4.w << 16);
+            const unsigned a = (w4.x >> 16) | (w4.y & J_SUM), b = (w4.z >> 16) | (w4.w & J_SUM);
             if (q4 + 3 < tw)
                 *reinterpret_cast<uint2 *>(dst) = make_uint2(a, b);
             else {
                 const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
                 for (int j = 0; j < 4 && q4 + j < tw; j++)
-                    dst[j] = (uint16_t)w[j];
+                    dst[j] = (uint16_t)(w[j] >> 16);
             }
         }
     }
