@@ -413,13 +413,12 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // ===========================================================================
 // Count modes (cell counts, taint counts): lean integer kernels.
 //   stage A  acc_local_cnt_kernel : subtree sums over the tile's forest by
-//            POINTER DOUBLING in shared memory.  One 32-bit word per cell,
-//                [31:16] sum over the 2^k cells upstream | [13:2] the cell 2^k steps
-//                downstream (active) or the root of the cell's path (done; a root
-//                points at itself) -- with the two flag bits masked off this is the
-//                byte offset of that cell's word | [1] root | [0] active,
-//            round k: every active cell hands its sum to the cell 2^k steps
-//            downstream (one shared atomic into `delta`) and doubles its pointer;
+//            POINTER DOUBLING.  Per cell a 16-bit pointer entry in shared memory,
+//                [12:1] the cell 2^k steps downstream (active) or the root of the
+//                cell's path (done; a root points at itself) | [0] active,
+//            and, in registers of the owning thread, the sum over the 2^k cells
+//            upstream.  Round k: every active cell hands its sum to the cell 2^k
+//            steps downstream (one shared atomic into `arr`) and doubles its pointer;
 //            ~log2(longest path) rounds, every lane busy in every round -- a
 //            river trunk is never walked cell by cell.  The rounds leave, for
 //            every cell, its tile-local count (u16 -> stage C) and the cell its
@@ -432,12 +431,12 @@ acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // ht_dir_pack_i8 by flagging the others EDGE), so no target is re-checked here.
 // ===========================================================================
 constexpr unsigned FLAGS_STOP = HT_DIR_NEG | HT_DIR_EDGE | HT_DIR_NULL;
-constexpr unsigned J_SUM = 0xFFFF0000u, J_PTR = 0x00003FFCu, J_ACTIVE = 1u, J_ROOT = 2u;
+constexpr unsigned J_PTR = 0x1FFEu, J_ACTIVE = 1u;
 constexpr int MAX_ROUNDS = 13; // 2^13 > T*T: only a cyclic (invalid) direction grid gets here
 
-constexpr int SMC_LO = SM_EFF;                   // uint32[T*T] cell words
-constexpr int SMC_DELTA = SMC_LO + T * T * 4;    // uint32[T*T] sums handed over in a round
-constexpr int SMC_LUT = SMC_DELTA + T * T * 4;   // uint32[16] code -> pointer step | active
+constexpr int SMC_PTR = SM_EFF;                  // uint16[T*T] pointer entries
+constexpr int SMC_ARR = SMC_PTR + T * T * 2;     // uint32[T*T] sums that arrived at a cell
+constexpr int SMC_LUT = SMC_ARR + T * T * 4;     // uint32[16] code -> pointer step | active
 constexpr int SMC_BAR = SMC_LUT + 64;            // mbarrier, then counters
 constexpr int SMC_TOTAL = SMC_BAR + 32;
 
@@ -485,13 +484,15 @@ __device__ __forceinline__ bool leaves_tile(unsigned b, int ly, int lx, int th, 
 }
 
 template <int WMODE>
-__global__ void __launch_bounds__(THREADS, 5)
+__global__ void __launch_bounds__(THREADS, 4)
 acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *pk = smem_raw;
-    uint32_t *word = reinterpret_cast<uint32_t *>(smem_raw + SMC_LO);
-    uint32_t *delta = reinterpret_cast<uint32_t *>(smem_raw + SMC_DELTA);
+    unsigned char *ptrb = smem_raw + SMC_PTR;   // uint16[T*T]
+    unsigned char *arrb = smem_raw + SMC_ARR;   // uint32[T*T]
+    uint16_t *ptr16 = reinterpret_cast<uint16_t *>(ptrb);
+    uint32_t *arr = reinterpret_cast<uint32_t *>(arrb);
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMC_LUT);
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMC_BAR);
     int *ctl = reinterpret_cast<int *>(smem_raw + SMC_BAR + 8); // [0] entries of the tile, [1] their place in the list
@@ -507,119 +508,93 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         ht::mbar_expect_tx(&bar, RH * RP);
         ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
     }
-    if (tid < 16) // added to a cell's own byte offset; codes 0, 9..15 make a root
-        lut[tid] = link_offset_of(tid) ? (unsigned)(link_offset_of(tid) * 4) + J_ACTIVE : J_ROOT;
+    if (tid < 16) // added to 2 * (cell index); codes 0, 9..15 never link
+        lut[tid] = link_offset_of(tid) ? (unsigned)(link_offset_of(tid) * 2) + J_ACTIVE : 0u;
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
-    // thread -> 4 consecutive cells of a row, 4 passes of 16 rows
-    const int q4 = 4 * (tid & 15), r0 = tid >> 4;
-    const int cbase = r0 * T + q4;
+    // thread -> cells tid + 256 k: one column, every 4th row.  A warp covers 32
+    // consecutive cells of a row in every step (conflict-free own accesses).
+    const int lx = tid & (T - 1), ly0 = tid >> 6;
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-        *reinterpret_cast<uint4 *>(delta + cbase + i * 16 * T) = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = 0; k < CPT; k++)
+        arr[tid + k * THREADS] = 0u;
     __syncthreads();
     ht::mbar_wait(&bar, 0);
 
-    // ---- cell words: sum = own value, pointer = receiver inside the tile
-    bool mine_active = false;
+    // ---- per cell: low = pointer entry, a = sum to hand on, own = the cell's own value
+    unsigned low[CPT], a[CPT];
+    unsigned own = 0; // bit k: own value of cell k
     {
-        unsigned cm[4]; // codes that do not link from column q4 + j; bit 15: outside the raster
+        // codes that do not link from this column; bit 15: outside the raster; bit 0: code 0
+        const unsigned cm = (lx == 0 ? EX_W : 0u) | (lx == tw - 1 ? EX_E : 0u) | (lx >= tw ? 0xFFFFu : 0u) | 1u;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            cm[j] = (q4 + j == 0 ? EX_W : 0u) | (q4 + j == tw - 1 ? EX_E : 0u) |
-                    (q4 + j >= tw ? 0xFFFFu : 0u) | 1u; // bit 0: code 0 never links
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int ly = r0 + 16 * i;
-            const unsigned wq = *reinterpret_cast<const unsigned *>(pk + (ly + 1) * RP + XO + q4);
-            const unsigned rm = (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u) | (ly >= th ? 0xFFFFu : 0u);
-            const unsigned self = (unsigned)(cbase + i * 16 * T) * 4u; // byte offset of cell j = 0
-            unsigned wd[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned b = (wq >> (8 * j)) & 0xFFu;
-                const unsigned code = b & HT_DIR_CODE;
-                const unsigned ex = rm | cm[j];
-                // no link: a stop flag, or the receiver is outside the tile / the raster
-                const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
-                const bool valid = !(b & HT_DIR_NULL) && !(ex >> 15);
-                const unsigned val = WMODE == W_ONE ? (valid ? 1u : 0u)
-                                                    : ((valid && (b & HT_DIR_TAINT)) ? 1u : 0u);
-                wd[j] = self + 4u * j + (stop ? J_ROOT : lut[code]) + (val << 16);
-                mine_active |= !stop;
-            }
-            *reinterpret_cast<uint4 *>(word + cbase + i * 16 * T) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        for (int k = 0; k < CPT; k++) {
+            const int ly = ly0 + 4 * k;
+            const unsigned b = pk[(ly + 1) * RP + XO + lx];
+            const unsigned ex = cm | (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u) | (ly >= th ? 0xFFFFu : 0u);
+            const unsigned code = b & HT_DIR_CODE;
+            // no link: a stop flag, or the receiver is outside the tile / the raster
+            const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
+            const bool valid = !(b & HT_DIR_NULL) && !(ex >> 15);
+            const unsigned val = WMODE == W_ONE ? (valid ? 1u : 0u) : ((valid && (b & HT_DIR_TAINT)) ? 1u : 0u);
+            own |= val << k;
+            a[k] = val;
+            low[k] = 2u * (unsigned)(tid + k * THREADS) + (stop ? 0u : lut[code]);
+            ptr16[tid + k * THREADS] = (uint16_t)low[k];
         }
     }
     __syncthreads();
 
-    // ---- pointer doubling
+    // ---- pointer doubling.  Only the pointer entries live in shared memory (they are
+    // what other cells read); sums arrive in arr[] and are snapshot into registers.
     for (int round = 0; round < MAX_ROUNDS; round++) {
-        unsigned np[16]; // low half (pointer, flags) of my cells after this round
-        if (mine_active) {
+        unsigned was = 0; // cells that were active in this round
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint4 w4 = *reinterpret_cast<const uint4 *>(word + cbase + i * 16 * T);
-                const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    unsigned n = w[j] & ~J_SUM;
-                    if (w[j] & J_ACTIVE) {
-                        const unsigned t = w[j] & J_PTR; // byte offset of the cell 2^k steps on
-                        const unsigned wt = *reinterpret_cast<const uint32_t *>(
-                            reinterpret_cast<const unsigned char *>(word) + t);
-                        const unsigned a = w[j] >> 16;
-                        if (WMODE == W_ONE || a)
-                            atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(delta) + t), a);
-                        // t still active: its pointer is 2^(k+1) steps from me; else I am done
-                        // and keep the root of the path (t's pointer; a root points at itself)
-                        n = wt & (J_PTR | J_ACTIVE);
-                    }
-                    np[4 * i + j] = n;
-                }
+        for (int k = 0; k < CPT; k++) {
+            if (low[k] & J_ACTIVE) {
+                const unsigned t2 = low[k] & J_PTR; // 2 * (cell 2^k steps downstream)
+                const unsigned wt = *reinterpret_cast<const uint16_t *>(ptrb + t2);
+                if (WMODE == W_ONE || a[k])
+                    atomicAdd(reinterpret_cast<uint32_t *>(arrb + 2 * t2), a[k]);
+                // t still active: its pointer is 2^(k+1) steps from me; else I am done and
+                // keep the root of the path (t's pointer; a root points at itself)
+                low[k] = wt;
+                was |= 1u << k;
             }
         }
         __syncthreads();
         bool still = false;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint4 d4 = *reinterpret_cast<const uint4 *>(delta + cbase + i * 16 * T);
-            if (!mine_active && !(d4.x | d4.y | d4.z | d4.w))
-                continue;
-            uint4 w4 = *reinterpret_cast<const uint4 *>(word + cbase + i * 16 * T);
-            if (mine_active) {
-                w4.x = np[4 * i + 0] | (w4.x & J_SUM);
-                w4.y = np[4 * i + 1] | (w4.y & J_SUM);
-                w4.z = np[4 * i + 2] | (w4.z & J_SUM);
-                w4.w = np[4 * i + 3] | (w4.w & J_SUM);
-                still |= ((w4.x | w4.y | w4.z | w4.w) & J_ACTIVE) != 0;
+        for (int k = 0; k < CPT; k++) {
+            if ((was >> k) & 1u) {
+                ptr16[tid + k * THREADS] = (uint16_t)low[k];
+                if (low[k] & J_ACTIVE) {
+                    a[k] = ((own >> k) & 1u) + arr[tid + k * THREADS];
+                    still = true;
+                }
             }
-            w4.x += d4.x << 16; w4.y += d4.y << 16; w4.z += d4.z << 16; w4.w += d4.w << 16;
-            *reinterpret_cast<uint4 *>(word + cbase + i * 16 * T) = w4;
-            if (d4.x | d4.y | d4.z | d4.w)
-                *reinterpret_cast<uint4 *>(delta + cbase + i * 16 * T) = make_uint4(0u, 0u, 0u, 0u);
         }
-        mine_active = still;
         if (!__syncthreads_or(still))
             break;
     }
 
     // ---- boundary graph.  thread -> one perimeter slot
     {
-        int ly = 0, lx = 0;
-        const bool per = perimeter_cell(tid, th, tw, ly, lx);
-        const unsigned b = per ? pk[(ly + 1) * RP + lx + XO] : (unsigned)HT_DIR_NULL;
+        int ly = 0, plx = 0;
+        const bool per = perimeter_cell(tid, th, tw, ly, plx);
+        const unsigned b = per ? pk[(ly + 1) * RP + plx + XO] : (unsigned)HT_DIR_NULL;
         // flow that leaves the tile through this cell
-        if (per && leaves_tile(b, ly, lx, th, tw)) {
-            const unsigned val = word[ly * T + lx] >> 16;
+        if (per && leaves_tile(b, ly, plx, th, tw)) {
+            const unsigned self = WMODE == W_ONE ? 1u : ((b & HT_DIR_TAINT) ? 1u : 0u);
+            const unsigned val = self + arr[ly * T + plx];
             if (val)
                 atomicAdd(reinterpret_cast<unsigned long long *>(p.base) +
-                              exit_slot(p, tx, ty, ly, lx, (int)(b & HT_DIR_CODE)),
+                              exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE)),
                           (unsigned long long)val);
         }
         // entry cell: a cell outside the tile drains into it
         bool entry = false;
         if (per && !(b & HT_DIR_NULL)) {
-            const int yy = ly + 1, xx = lx + XO;
+            const int yy = ly + 1, xx = plx + XO;
 #pragma unroll
             for (int kk = 0; kk < 9; kk++) {
                 if (kk == 4)
@@ -642,8 +617,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         __syncthreads();
         if (entry) {
             // where the path that enters here leaves the tile: the root of the cell
-            const unsigned w = word[ly * T + lx];
-            const int rc = (int)((w & J_PTR) >> 2), cy = rc >> 6, cx = rc & (T - 1);
+            const int rc = (int)(ptr16[ly * T + plx] >> 1), cy = rc >> 6, cx = rc & (T - 1);
             const unsigned rb = pk[(cy + 1) * RP + cx + XO];
             const int32_t slot = tile * SLOTS + tid;
             p.list[ctl[1] + at] = slot;
@@ -653,27 +627,16 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         }
     }
 
-    // ---- tile-local counts for stage C (u16, 8-byte stores)
-    {
-        uint16_t *dst = p.lacc + (y0 + r0) * p.lacc_ld + x0 + q4;
-        const int64_t step = 16 * p.lacc_ld;
+    // ---- tile-local counts for stage C (u16; a warp stores 64 consecutive bytes)
+    if (lx < tw) {
+        uint16_t *dst = p.lacc + (y0 + ly0) * p.lacc_ld + x0 + lx;
+        const int64_t step = 4 * p.lacc_ld;
 #pragma unroll
-        for (int i = 0; i < 4; i++, dst += step) {
-            if (r0 + 16 * i >= th || q4 >= tw)
-                continue;
-            const uint4 w4 = *reinterpret_cast<const uint4 *>(word + cbase + i * 16 * T);
-            const unsigned a = (w4.x >> 16) | (w4.y & J_SUM), b = (w4.z >> 16) | (w4.w & J_SUM);
-            if (q4 + 3 < tw)
-                *reinterpret_cast<uint2 *>(dst) = make_uint2(a, b);
-            else {
-                const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
-                for (int j = 0; j < 4 && q4 + j < tw; j++)
-                    dst[j] = (uint16_t)(w[j] >> 16);
-            }
-        }
+        for (int k = 0; k < CPT; k++, dst += step)
+            if (ly0 + 4 * k < th)
+                *dst = (uint16_t)(((own >> k) & 1u) + arr[tid + k * THREADS]);
     }
 }
-
 
 // stage C cell words: lo32 = [31:24] signed receiver offset inside the tile (0 =
 // none) | [23:0] low part of the count; hi32 = count >> 16.  A walker adds its
