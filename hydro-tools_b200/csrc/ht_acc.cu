@@ -841,11 +841,22 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch)
     __syncthreads();
 }
 
+// Subtree sums over a forest, nodes renumbered densely (node id = position in
+// `list`; identity when there is no list) so that a round touches, per node,
+// two coalesced streams of its own state plus TWO random accesses: the pointer of
+// the node 2^k steps downstream and the atomic that hands the sum on.
+//   round k: node i hands a[i] (sum over the 2^k nodes upstream of it, itself
+//   included) to t = ptr[i] and doubles its pointer, ptr'[i] = ptr[t].
+// Sums handed over in round k land in arr[k & 1]; the owner folds them into a[i]
+// at the start of round k + 1 (nobody writes that buffer then) -- one grid
+// barrier per round.  A node whose pointer has run off the end of its path is
+// done; what still arrives for it stays in arr[] and is added at the very end.
 template <typename V>
 __global__ void __launch_bounds__(256, 4)
-coarse_resolve_kernel(const V *base0, const int32_t *next0, V *agg, V *delta, int32_t *ptrA,
-                      int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n,
-                      const int32_t *list, const int *nlist, int *flags, int *rounds_out)
+coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int32_t *list,
+                      const int *nlist, int32_t *idmap, int32_t *ptrA, int32_t *ptrB, V *a,
+                      V *arr0, V *arr1, int32_t *rootA, int32_t *rootB, V *agg_out,
+                      int32_t *root_out, int *flags, int *rounds_out)
 {
     unsigned *gbar = reinterpret_cast<unsigned *>(flags + 96); // zeroed with flags
     unsigned epoch = 0;
@@ -853,86 +864,82 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, V *agg, V *delta, in
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // only the slots in `list` are nodes (all n slots if there is no list)
     const int64_t na = list ? (int64_t)*nlist : n;
-    // The graph itself (base0 / next0) is left untouched so that it can be resolved
-    // again after inflow from other bands has been added.  `delta` arrives zeroed.
-    if (rootA)
-        for (int64_t u = t0; u < n; u += stride)
-            rootB[u] = (int32_t)u; // slots that are not nodes end at themselves
+    if (list) {
+        for (int64_t i = t0; i < na; i += stride)
+            idmap[list[i]] = (int32_t)i;
+        if (root_out)
+            for (int64_t s = t0; s < n; s += stride)
+                root_out[s] = (int32_t)s; // slots that are not nodes end at themselves
+        grid_barrier(gbar, epoch);
+    }
     for (int64_t i = t0; i < na; i += stride) {
         const int64_t u = list ? list[i] : i;
-        agg[u] = base0[u];
-        ptrA[u] = next0[u];
+        const int32_t nx = next0[u];
+        ptrA[i] = nx < 0 ? -1 : (list ? idmap[nx] : nx);
+        a[i] = base0[u];
+        arr0[i] = (V)0;
+        arr1[i] = (V)0;
         if (rootA)
-            rootA[u] = (int32_t)u;
+            rootA[i] = (int32_t)i;
     }
     grid_barrier(gbar, epoch);
-    // round k: agg[v] holds the sum over the nodes within 2^k - 1 steps upstream of v
-    // (v included), ptr[u] the node 2^k steps downstream of u.
-    //   phase 1: every u hands agg[u] to ptr[u] through `delta`, ptr[u] <- ptr[ptr[u]]
-    //   phase 2: agg += delta, delta <- 0
+
     int round = 0;
     for (;; round++) {
+        V *cur = (round & 1) ? arr1 : arr0, *prev = (round & 1) ? arr0 : arr1;
         bool any = false;
         constexpr int U = 4; // independent nodes in flight per thread
         for (int64_t i0 = t0; i0 < na; i0 += stride * U) {
-            int32_t u[U], q[U], qq[U], rr[U];
-            V a[U];
+            int32_t t[U], pt[U], rr[U];
+            V v[U], d[U];
 #pragma unroll
             for (int j = 0; j < U; j++) {
                 const int64_t i = i0 + j * stride;
-                u[j] = i < na ? (list ? list[i] : (int32_t)i) : -1;
+                t[j] = i < na ? ptrA[i] : -2; // -2: no such node
             }
 #pragma unroll
-            for (int j = 0; j < U; j++)
-                q[j] = u[j] >= 0 ? ptrA[u[j]] : -1;
-#pragma unroll
             for (int j = 0; j < U; j++) {
-                qq[j] = q[j] >= 0 ? ptrA[q[j]] : q[j];
-                a[j] = q[j] >= 0 ? agg[u[j]] : (V)0;
+                const int64_t i = i0 + j * stride;
+                pt[j] = t[j] >= 0 ? ptrA[t[j]] : -1;
+                v[j] = t[j] >= 0 ? a[i] : (V)0;
+                d[j] = t[j] >= 0 ? prev[i] : (V)0;
                 if (rootA)
-                    rr[j] = u[j] >= 0 ? rootA[q[j] >= 0 ? q[j] : u[j]] : 0;
+                    rr[j] = t[j] >= 0 ? rootA[t[j]] : (t[j] == -1 ? rootA[i] : 0);
             }
 #pragma unroll
             for (int j = 0; j < U; j++) {
-                if (u[j] < 0)
+                const int64_t i = i0 + j * stride;
+                if (t[j] == -2)
                     continue;
-                if (q[j] >= 0) {
-                    if (a[j] != (V)0)
-                        atomic_add_v(&delta[q[j]], a[j]);
+                if (t[j] >= 0) {
+                    if (d[j] != (V)0) { // what arrived in the last round
+                        v[j] += d[j];
+                        a[i] = v[j];
+                        prev[i] = (V)0;
+                    }
+                    if (v[j] != (V)0)
+                        atomic_add_v(&cur[t[j]], v[j]);
                     any = true;
                 }
-                ptrB[u[j]] = qq[j];
+                ptrB[i] = pt[j];
                 if (rootA)
-                    rootB[u[j]] = rr[j];
+                    rootB[i] = rr[j];
             }
         }
         if (any)
             flags[round] = 1;
         grid_barrier(gbar, epoch);
-        const bool more = flags[round] != 0;
-        if (more) {
-            for (int64_t i = t0; i < na; i += stride) {
-                const int64_t u = list ? list[i] : i;
-                const V d = delta[u];
-                if (d != (V)0) {
-                    agg[u] += d;
-                    delta[u] = (V)0;
-                }
-            }
-        }
         int32_t *tp = ptrA; ptrA = ptrB; ptrB = tp;
         tp = rootA; rootA = rootB; rootB = tp;
-        if (!more || round == 62)
+        if (!flags[round] || round == 62)
             break;
-        grid_barrier(gbar, epoch);
     }
-    // the caller reads the last node of every path from its "rootB": after
-    // round + 1 swaps that is the local rootA when the count is odd
-    if (rootA && (round & 1)) {
-        for (int64_t i = t0; i < na; i += stride) {
-            const int64_t u = list ? list[i] : i;
-            rootB[u] = rootA[u];
-        }
+    // totals (and the last node of every path) back to slot order
+    for (int64_t i = t0; i < na; i += stride) {
+        const int64_t u = list ? list[i] : i;
+        agg_out[u] = a[i] + arr0[i] + arr1[i];
+        if (rootA && root_out)
+            root_out[u] = list ? list[rootA[i]] : rootA[i];
     }
     if (t0 == 0 && rounds_out)
         *rounds_out = round + 1;
@@ -951,8 +958,8 @@ __global__ void append_range_kernel(int32_t *list, int *nlist, int32_t first, in
 struct Workspace {
     uint16_t *lacc;
     int64_t lacc_ld;
-    void *base0, *aggA, *aggB;
-    int32_t *next0, *ptrA, *ptrB, *rootA, *rootB, *list;
+    void *base0, *aggA, *aggB, *arr0, *arr1;
+    int32_t *next0, *ptrA, *ptrB, *rootA, *rootB, *list, *idmap, *rootC;
     int *flags, *nlist;
     int64_t nslots;
 };
@@ -968,7 +975,7 @@ size_t workspace_bytes(int64_t rows, int64_t cols)
 {
     const int64_t n = nslots_of(rows, cols);
     const int64_t lacc_ld = (cols + 7) / 8 * 8;
-    return 3 * align_up(n * 8) + 6 * align_up(n * 4) + align_up(128 * sizeof(int)) +
+    return 5 * align_up(n * 8) + 8 * align_up(n * 4) + align_up(128 * sizeof(int)) +
            align_up((size_t)rows * lacc_ld * 2) + 256;
 }
 
@@ -987,6 +994,10 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
     w.rootA = (int32_t *)b; b += align_up(n * 4);
     w.rootB = (int32_t *)b; b += align_up(n * 4);
     w.list = (int32_t *)b; b += align_up(n * 4);
+    w.idmap = (int32_t *)b; b += align_up(n * 4);
+    w.rootC = (int32_t *)b; b += align_up(n * 4);
+    w.arr0 = b; b += align_up(n * 8);
+    w.arr1 = b; b += align_up(n * 8);
     w.flags = (int *)b; b += align_up(128 * sizeof(int));
     w.nlist = w.flags + 64;
     w.lacc = (uint16_t *)b;
@@ -1045,11 +1056,14 @@ int dispatch_tile(int mode, const CUtensorMap &map, const AccArgs &p, cudaStream
     return HT_ERR_ARG;
 }
 
+// agg_out[n] (slot order) must arrive zeroed where a slot is not a node.  Scratch:
+// a / arr0 / arr1 (n values each), ptrA / ptrB (n), idmap (n, only with a list),
+// rootA / rootB (n each, only with root_out).
 template <typename V>
-int launch_resolve(const void *base0, const int32_t *next0, void *agg_, void *delta_,
-                   int32_t *ptrA, int32_t *ptrB, int32_t *rootA, int32_t *rootB, int64_t n,
-                   const int32_t *list, const int *nlist, int *flags, int *rounds_dev,
-                   cudaStream_t st)
+int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int32_t *list,
+                   const int *nlist, int32_t *idmap, int32_t *ptrA, int32_t *ptrB, void *a_,
+                   void *arr0_, void *arr1_, int32_t *rootA, int32_t *rootB, void *agg_out_,
+                   int32_t *root_out, int *flags, int *rounds_dev, cudaStream_t st)
 {
     auto kern = coarse_resolve_kernel<V>;
     int per_sm = 0;
@@ -1066,10 +1080,9 @@ int launch_resolve(const void *base0, const int32_t *next0, void *agg_, void *de
     HT_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));      // per-round flags
     HT_CUDA_TRY(cudaMemsetAsync(flags + 96, 0, sizeof(int), st));      // grid barrier counter
     const V *b0 = (const V *)base0;
-    // result lands in `agg`; `delta` is scratch and must start at zero
-    HT_CUDA_TRY(cudaMemsetAsync(delta_, 0, n * 8, st));
-    V *agg = (V *)agg_, *delta = (V *)delta_;
-    void *args[] = {&b0, &next0, &agg, &delta, &ptrA, &ptrB, &rootA, &rootB, &n, &list, &nlist, &flags, &rounds_dev};
+    V *a = (V *)a_, *arr0 = (V *)arr0_, *arr1 = (V *)arr1_, *agg_out = (V *)agg_out_;
+    void *args[] = {&b0, &next0, &n, &list, &nlist, &idmap, &ptrA, &ptrB, &a, &arr0, &arr1,
+                    &rootA, &rootB, &agg_out, &root_out, &flags, &rounds_dev};
     HT_CUDA_TRY(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(256), args, 0, st));
     return 0;
 }
@@ -1152,15 +1165,18 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
     int rc = carve(ws, ws_bytes, rows, cols, wk);
     if (rc)
         return rc;
-    int32_t *rA = want_roots ? wk.rootA : nullptr, *rB = want_roots ? wk.rootB : nullptr;
+    // rootB is the slot-ordered output ("last node of each slot's path")
+    int32_t *rA = want_roots ? wk.rootA : nullptr, *rC = want_roots ? wk.rootC : nullptr;
+    int32_t *rOut = want_roots ? wk.rootB : nullptr;
     HT_CUDA_TRY(cudaMemsetAsync(wk.aggB, 0, wk.nslots * 8, (cudaStream_t)stream));
     if (mode == W_F32)
-        return launch_resolve<double>(wk.base0, wk.next0, wk.aggB, wk.aggA, wk.ptrA, wk.ptrB, rA,
-                                      rB, wk.nslots, wk.list, wk.nlist, wk.flags, rounds_dev,
-                                      (cudaStream_t)stream);
-    return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.aggB, wk.aggA, wk.ptrA,
-                                              wk.ptrB, rA, rB, wk.nslots, wk.list, wk.nlist,
-                                              wk.flags, rounds_dev, (cudaStream_t)stream);
+        return launch_resolve<double>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist, wk.idmap,
+                                      wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1, rA, rC, wk.aggB,
+                                      rOut, wk.flags, rounds_dev, (cudaStream_t)stream);
+    return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist,
+                                              wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
+                                              rA, rC, wk.aggB, rOut, wk.flags, rounds_dev,
+                                              (cudaStream_t)stream);
 }
 
 // Byte offsets (from the workspace pointer) of the boundary-graph arrays, for the
@@ -1196,19 +1212,23 @@ extern "C" int ht_forest_resolve(const void *base, const int32_t *next, int64_t 
         return HT_OK;
     if (!base || !next || !agg_out || !tmp || n < 0)
         return HT_ERR_ARG;
-    const size_t need = align_up(n * 8) + 2 * align_up(n * 4) + 512 + 256;
+    const size_t need = 3 * align_up(n * 8) + 2 * align_up(n * 4) + 512 + 256;
     if (tmp_bytes < need)
         return HT_ERR_WORKSPACE;
     uint8_t *b = (uint8_t *)(((uintptr_t)tmp + 255) / 256 * 256);
-    void *aggA = b; b += align_up(n * 8);
+    void *a = b; b += align_up(n * 8);
+    void *arr0 = b; b += align_up(n * 8);
+    void *arr1 = b; b += align_up(n * 8);
     int32_t *ptrA = (int32_t *)b; b += align_up(n * 4);
     int32_t *ptrB = (int32_t *)b; b += align_up(n * 4);
     int *flags = (int *)b;
     if (is_f64)
-        return launch_resolve<double>(base, next, agg_out, aggA, ptrA, ptrB, nullptr, nullptr, n,
-                                      nullptr, nullptr, flags, nullptr, (cudaStream_t)stream);
-    return launch_resolve<unsigned long long>(base, next, agg_out, aggA, ptrA, ptrB, nullptr, nullptr,
-                                              n, nullptr, nullptr, flags, nullptr, (cudaStream_t)stream);
+        return launch_resolve<double>(base, next, n, nullptr, nullptr, nullptr, ptrA, ptrB, a, arr0,
+                                      arr1, nullptr, nullptr, agg_out, nullptr, flags, nullptr,
+                                      (cudaStream_t)stream);
+    return launch_resolve<unsigned long long>(base, next, n, nullptr, nullptr, nullptr, ptrA, ptrB, a,
+                                              arr0, arr1, nullptr, nullptr, agg_out, nullptr, flags,
+                                              nullptr, (cudaStream_t)stream);
 }
 
 

@@ -306,7 +306,7 @@ class CudaBand:
     def forest_resolve(self, base, nxt, mode=0):
         n = base.numel()
         out = torch.empty_like(base)
-        need = 16 * n + 4096
+        need = 32 * n + 8192
         if self._tmp is None or self._tmp.numel() < need:
             self._tmp = torch.empty(need, dtype=torch.uint8, device=self.dev)
         self.N.call("ht_forest_resolve", base.data_ptr(), nxt.data_ptr(), n,

@@ -117,7 +117,7 @@ int ht_acc_workspace_layout(int64_t rows, int64_t cols, void *ws, size_t ws_byte
                             int64_t *layout11_host);
 /* subtree sums over a forest given by next[] (< 0 = root); the band-level
  * boundary graph of a row-band sharded raster is resolved with it.
- * tmp_bytes >= 16*n + 2048. */
+ * tmp_bytes >= 32*n + 4096. */
 int ht_forest_resolve(const void *base, const int32_t *next, int64_t n, int is_f64,
                       void *agg_out, void *tmp, size_t tmp_bytes, void *stream);
 int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
