@@ -70,12 +70,6 @@ __device__ __forceinline__ int ct2code(int ct) { return (0x37518426u >> (4 * ct)
 // GRASS direction code that points at window cell k = {3, 2, 1, 4, 0, 8, 5, 6, 7}
 __device__ __forceinline__ int win2code(int k) { return (int)((0x765804123ULL >> (4 * k)) & 0xF); }
 
-// rule R1: (int)(z*1000 +- 0.5) in double, as GRASS ele_round(); d = z * 1000
-__device__ __forceinline__ int32_t alt_from_f64(double d)
-{
-    return (int32_t)(d > 0 ? d + 0.5 : d - 0.5);
-}
-
 // is fl(a/da) < fl(b/db) in double?  fp32 filter first (relative slack 1e-6
 // dwarfs the 2e-7 float error), exact GRASS arithmetic only when it is close.
 __device__ __forceinline__ bool slope_less(int32_t a, double da, float inv_da, int32_t b,
@@ -229,7 +223,8 @@ __device__ __forceinline__ int d8_plain_cell(float w0, float w1, float w2, float
         const float m = fminf(s_ew, s_ns);
         const float e = d - m; // > 0: a flank is steeper, the diagonal is skipped
         t_amb = fminf(t_amb, fmaf(-EPS, fabsf(m), fabsf(e)));
-        return e > 0.0f ? BLOCKED : fmaf(d, 8.0f, ct);
+        // e > 0 pushes the key out of reach (e >= 2^-19 whenever it is not ambiguous)
+        return fmaf(fmaxf(e, 0.0f), BLOCKED, fmaf(d, 8.0f, ct));
     };
     const float k0 = fmaf(dS, 8.0f, 0.0f), k1 = fmaf(dN, 8.0f, 1.0f);
     const float k2 = fmaf(dW, 8.0f, 2.0f), k3 = fmaf(dE, 8.0f, 3.0f);
@@ -307,18 +302,22 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
                 float *z = reinterpret_cast<float *>(&q);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const bool null = (p.has_nodata && z[j] == p.nodata) || z[j] != z[j];
+                    // |z| < 16 777.2 m  =>  |alt| < 2^24 - 15; false for NaN
+                    const bool small = fabsf(z[j]) < 16777.2f;
+                    const bool nd = p.has_nodata && z[j] == p.nodata;
                     float a = F_INVALID;
-                    if (!null) {
-                        const double d = (double)z[j] * 1000.0;
-                        if (fabs(d) < 16777215.0)
-                            a = (float)alt_from_f64(d);
-                        else {
-                            a = d > 0 ? (float)(ALT_LIMIT - 1) : (float)(1 - ALT_LIMIT);
-                            range++;
-                        }
+                    if (small && !nd) {
+                        // rule R1: (int)(z * 1000 +- 0.5) in double; the half takes z's sign
+                        const double half = __hiloint2double(
+                            0x3FE00000 | (int)(__float_as_uint(z[j]) & 0x80000000u), 0);
+                        a = (float)(int)((double)z[j] * 1000.0 + half);
                     }
-                    saw_invalid |= null;
+                    else if (!nd && z[j] == z[j]) { // out of range: clamped and counted
+                        a = z[j] > 0 ? (float)(ALT_LIMIT - 1) : (float)(1 - ALT_LIMIT);
+                        range++;
+                    }
+                    else
+                        saw_invalid = true;
                     z[j] = a;
                 }
                 box[i] = q;
