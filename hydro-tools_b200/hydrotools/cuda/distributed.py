@@ -336,9 +336,9 @@ class CudaBand:
     def time_kernels(self, iters=5):
         """Average device time of each stage (CUDA events on the launching stream)."""
         stages = [("d8_kernel", self.direction),
-                  ("acc_tile_kernel<local>", lambda: self.local(0)),
+                  ("acc_local_cnt_kernel", lambda: self.local(0)),
                   ("coarse_resolve_kernel", lambda: self.resolve(False)),
-                  ("acc_tile_kernel<final>", lambda: self.final(0))]
+                  ("acc_final_cnt_kernel", lambda: self.final(0))]
         out = []
         for name, fn in stages:
             fn()

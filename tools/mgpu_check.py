@@ -35,6 +35,6 @@ for nulls in (False, True):
         es, _, _ = oracle.gdaldem(dem, -32767.0 if nulls else None, 10.0, 10.0)
         got = torch.cat(gs).cpu().numpy()
         ok = es != -9999
-        print("  terrain slope max rel err", np.abs(got[ok] - es[ok]).max(), "mask equal", np.array_equal(got == -9999, ~ok))
+        print("  terrain slope max abs err (degrees)", np.abs(got[ok] - es[ok]).max(), "mask equal", np.array_equal(got == -9999, ~ok))
 dist.barrier()
 dist.destroy_process_group()

@@ -1,0 +1,52 @@
+"""Development aid (torchrun): device time of every phase of the row-band
+sharded D8 + accumulation step."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hydro-tools_b200"))
+import torch, torch.distributed as dist
+from hydrotools.cuda import distributed as HD
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+rows = cols = 10000
+eng = HD.BandEngine(rank, world, rows, cols, rows * world, 10.0, 10.0)
+eng.generate_synthetic(20261019)
+band = eng.band
+for _ in range(3):
+    eng.flow_direction_accumulation()
+torch.cuda.synchronize(); dist.barrier()
+
+marks = []
+def mark(name):
+    e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
+
+tot = {}
+for it in range(10):
+    marks.clear()
+    mark("start")
+    eng.exchange_halos(2); mark("halo exchange")
+    band.direction(); mark("d8")
+    band.local(0); mark("stage A")
+    band.resolve(True); mark("stage B (roots)")
+    delivered, link = band.band_tables(0); mark("band tables")
+    P = world
+    all_d = torch.empty((P * 2, cols), dtype=delivered.dtype, device=delivered.device)
+    all_l = torch.empty((P * 2, cols), dtype=link.dtype, device=link.device)
+    dist.all_gather_into_tensor(all_d, delivered.contiguous())
+    dist.all_gather_into_tensor(all_l, link.contiguous()); mark("all_gather x2")
+    base, nxt = HD.build_band_graph(all_d.view(P, 2, cols), all_l.view(P, 2, cols)); mark("build band graph")
+    inflow = band.forest_resolve(base, nxt, 0).view(P, 2, cols); mark("band forest resolve")
+    band.add_inflow(inflow[rank, 0], inflow[rank, 1], 0); mark("add inflow")
+    band.resolve(False); mark("stage B again")
+    band.final(0); mark("stage C")
+    torch.cuda.synchronize()
+    for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+        tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
+dist.barrier()
+if rank == 0:
+    s = 0
+    for k, v in tot.items():
+        print(f"{k:24s} {v / 10:8.4f} ms"); s += v / 10
+    print(f"{'sum':24s} {s:8.4f} ms")
+dist.destroy_process_group()

@@ -42,9 +42,9 @@ METRICS = [
 BENCH_NAME = [
     (r"d8_kernel", "d8_kernel"),
     (r"acc_fused", "acc_fused_kernel"),
-    (r"acc_local", "acc_tile_kernel<local>"),
+    (r"acc_local", "acc_local_cnt_kernel"),
     (r"coarse_resolve", "coarse_resolve_kernel"),
-    (r"acc_final", "acc_tile_kernel<final>"),
+    (r"acc_final", "acc_final_cnt_kernel"),
     (r"terrain_kernel", "terrain_kernel"),
 ]
 
