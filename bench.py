@@ -24,6 +24,10 @@ import sys
 import threading
 import time
 
+# NCCL's version banner goes to stdout; the contract is ONE JSON line there
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "hydro-tools_b200"))
