@@ -851,12 +851,19 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch)
 // at the start of round k + 1 (nobody writes that buffer then) -- one grid
 // barrier per round.  A node whose pointer has run off the end of its path is
 // done; what still arrives for it stays in arr[] and is added at the very end.
+constexpr int MARK_SHIFT = 48; // band-edge marks ride in bits 48.. of the u64 sums
+__device__ __forceinline__ unsigned long long masked_plus(unsigned long long old, unsigned long long add)
+{
+    return (old & ((1ull << MARK_SHIFT) - 1ull)) + add;
+}
+__device__ __forceinline__ double masked_plus(double old, double add) { return old + add; }
+
 template <typename V>
 __global__ void __launch_bounds__(256, 4)
 coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int32_t *list,
                       const int *nlist, int32_t *idmap, int32_t *ptrA, int32_t *ptrB, V *a,
                       V *arr0, V *arr1, int32_t *rootA, int32_t *rootB, V *agg_out,
-                      int32_t *root_out, int *flags, int *rounds_out)
+                      int32_t *root_out, int *flags, int *rounds_out, int add_to_masked)
 {
     unsigned *gbar = reinterpret_cast<unsigned *>(flags + 96); // zeroed with flags
     unsigned epoch = 0;
@@ -937,7 +944,10 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
     // totals (and the last node of every path) back to slot order
     for (int64_t i = t0; i < na; i += stride) {
         const int64_t u = list ? list[i] : i;
-        agg_out[u] = a[i] + arr0[i] + arr1[i];
+        const V total = a[i] + arr0[i] + arr1[i];
+        // delta resolve: the totals are a correction on top of an earlier result whose
+        // upper 16 bits carried band-edge marks (u64 values only)
+        agg_out[u] = add_to_masked ? masked_plus(agg_out[u], total) : total;
         if (rootA && root_out)
             root_out[u] = list ? list[rootA[i]] : rootA[i];
     }
@@ -955,11 +965,55 @@ __global__ void append_range_kernel(int32_t *list, int *nlist, int32_t first, in
         list[base + i] = first + i;
 }
 
+// Row-band sharding, delta resolve: the nodes whose resolved sum carries a mark lie
+// on or downstream of a band-edge cell, i.e. they are the only ones whose inflow
+// changes when the neighbour bands' deliveries come in.  They are closed under
+// next[]: a forest of their own, resolved with base = the imported flow.
+__global__ void marked_nodes_kernel(const unsigned long long *agg, const int32_t *list,
+                                    const int *nlist, int32_t *list2, int *nlist2,
+                                    unsigned long long *base2, const unsigned long long *imp_top,
+                                    const unsigned long long *imp_bot, int64_t rows, int64_t cols,
+                                    int tiles_x, int tiles_y)
+{
+    const int na = *nlist;
+    const int lane = threadIdx.x & 31;
+    const int last_h = (int)(rows - (int64_t)(tiles_y - 1) * T);
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < na; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        const int32_t u = i < na ? list[i] : 0;
+        const bool in = i < na && (agg[u] >> MARK_SHIFT) != 0ull;
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (!m)
+            continue;
+        int at = 0;
+        if (lane == 0)
+            at = atomicAdd(nlist2, __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+        if (in) {
+            list2[at] = u;
+            unsigned long long b = 0ull;
+            const int tile = u / SLOTS, k = u % SLOTS;
+            if (tile < tiles_x * tiles_y) { // not a virtual slot
+                const int ty = tile / tiles_x, tx = tile % tiles_x;
+                const int64_t col = (int64_t)tx * T + (k & (T - 1));
+                if (imp_top && ty == 0 && k < T && col < cols)
+                    b = imp_top[col];
+                else if (imp_bot && ty == tiles_y - 1 && col < cols &&
+                         (last_h == 1 ? k < T : (k >= T && k < 2 * T)))
+                    b = imp_bot[col];
+            }
+            base2[u] = b;
+        }
+    }
+}
+
 struct Workspace {
     uint16_t *lacc;
     int64_t lacc_ld;
     void *base0, *aggA, *aggB, *arr0, *arr1;
-    int32_t *next0, *ptrA, *ptrB, *rootA, *rootB, *list, *idmap, *rootC;
+    int32_t *next0, *ptrA, *ptrB, *rootA, *rootB, *list, *idmap, *rootC, *list2;
+    void *base2;
+    int *nlist2;
     int *flags, *nlist;
     int64_t nslots;
 };
@@ -975,7 +1029,7 @@ size_t workspace_bytes(int64_t rows, int64_t cols)
 {
     const int64_t n = nslots_of(rows, cols);
     const int64_t lacc_ld = (cols + 7) / 8 * 8;
-    return 5 * align_up(n * 8) + 8 * align_up(n * 4) + align_up(128 * sizeof(int)) +
+    return 6 * align_up(n * 8) + 9 * align_up(n * 4) + align_up(128 * sizeof(int)) +
            align_up((size_t)rows * lacc_ld * 2) + 256;
 }
 
@@ -996,10 +1050,13 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
     w.list = (int32_t *)b; b += align_up(n * 4);
     w.idmap = (int32_t *)b; b += align_up(n * 4);
     w.rootC = (int32_t *)b; b += align_up(n * 4);
+    w.list2 = (int32_t *)b; b += align_up(n * 4);
+    w.base2 = b; b += align_up(n * 8);
     w.arr0 = b; b += align_up(n * 8);
     w.arr1 = b; b += align_up(n * 8);
     w.flags = (int *)b; b += align_up(128 * sizeof(int));
     w.nlist = w.flags + 64;
+    w.nlist2 = w.flags + 65;
     w.lacc = (uint16_t *)b;
     w.lacc_ld = (cols + 7) / 8 * 8;
     w.nslots = n;
@@ -1063,7 +1120,8 @@ template <typename V>
 int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int32_t *list,
                    const int *nlist, int32_t *idmap, int32_t *ptrA, int32_t *ptrB, void *a_,
                    void *arr0_, void *arr1_, int32_t *rootA, int32_t *rootB, void *agg_out_,
-                   int32_t *root_out, int *flags, int *rounds_dev, cudaStream_t st)
+                   int32_t *root_out, int *flags, int *rounds_dev, cudaStream_t st,
+                   int add_to_masked = 0)
 {
     auto kern = coarse_resolve_kernel<V>;
     int per_sm = 0;
@@ -1082,7 +1140,7 @@ int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int
     const V *b0 = (const V *)base0;
     V *a = (V *)a_, *arr0 = (V *)arr0_, *arr1 = (V *)arr1_, *agg_out = (V *)agg_out_;
     void *args[] = {&b0, &next0, &n, &list, &nlist, &idmap, &ptrA, &ptrB, &a, &arr0, &arr1,
-                    &rootA, &rootB, &agg_out, &root_out, &flags, &rounds_dev};
+                    &rootA, &rootB, &agg_out, &root_out, &flags, &rounds_dev, &add_to_masked};
     HT_CUDA_TRY(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(256), args, 0, st));
     return 0;
 }
@@ -1177,6 +1235,38 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
                                               wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
                                               rA, rC, wk.aggB, rOut, wk.flags, rounds_dev,
                                               (cudaStream_t)stream);
+}
+
+// Row-band sharding, count modes.  ht_acc_resolve must have run on a boundary graph
+// whose band-edge slots carried a mark (1 << 48 added to base0); `imp_top` /
+// `imp_bot` (cols values each, or NULL) are the flows the neighbour bands deliver
+// into the cells of the band's first / last row.  Adds their effect to the resolved
+// inflow of every node downstream and clears the marks -- a resolve over the
+// marked nodes only instead of a second full one.
+extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
+                                    const unsigned long long *imp_top,
+                                    const unsigned long long *imp_bot, void *ws, size_t ws_bytes,
+                                    void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    if (mode == W_F32)
+        return HT_ERR_ARG; // marks need integer sums
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    if (rc)
+        return rc;
+    HT_CUDA_TRY(cudaMemsetAsync(wk.nlist2, 0, sizeof(int), st));
+    marked_nodes_kernel<<<ht::kSMs * 4, 256, 0, st>>>(
+        (const unsigned long long *)wk.aggB, wk.list, wk.nlist, wk.list2, wk.nlist2,
+        (unsigned long long *)wk.base2, imp_top, imp_bot, rows, cols, ht::cdiv(cols, T),
+        ht::cdiv(rows, T));
+    HT_LAUNCH_CHECK();
+    return launch_resolve<unsigned long long>(wk.base2, wk.next0, wk.nslots, wk.list2, wk.nlist2,
+                                              wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
+                                              nullptr, nullptr, wk.aggB, nullptr, wk.flags, nullptr,
+                                              st, 1);
 }
 
 // Byte offsets (from the workspace pointer) of the boundary-graph arrays, for the

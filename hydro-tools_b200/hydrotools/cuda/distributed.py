@@ -104,25 +104,19 @@ class BandEngine:
 
     # ----------------------------------------------------------------- comm
     def exchange_halos(self, depth: int):
-        """`depth` DEM rows to / from each band neighbour (send/recv pairs)."""
-        band, ops, recvs = self.band, [], []
+        """`depth` DEM rows to / from each band neighbour.  One all-gather of every
+        band's first and last `depth` rows (2 * depth * cols * 4 B per band): a single
+        collective costs less than two send/recv pairs, and over NVSwitch the extra
+        rows are free."""
+        band, P = self.band, self.world
+        send = torch.stack([band.edge_rows(top=True, depth=depth),
+                            band.edge_rows(top=False, depth=depth)])  # [2, depth, cols]
+        every = torch.empty((P,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(every.view(P * 2, depth, self.cols), send, group=self.group)
         if self.rank > 0:
-            send = band.edge_rows(top=True, depth=depth)
-            recv = torch.empty_like(send)
-            ops += [dist.P2POp(dist.isend, send, self.rank - 1, self.group),
-                    dist.P2POp(dist.irecv, recv, self.rank - 1, self.group)]
-            recvs.append((True, recv))
-        if self.rank < self.world - 1:
-            send = band.edge_rows(top=False, depth=depth)
-            recv = torch.empty_like(send)
-            ops += [dist.P2POp(dist.isend, send, self.rank + 1, self.group),
-                    dist.P2POp(dist.irecv, recv, self.rank + 1, self.group)]
-            recvs.append((False, recv))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        for top, recv in recvs:
-            band.set_halo_rows(top=top, rows=recv)
+            band.set_halo_rows(top=True, rows=every[self.rank - 1, 1])
+        if self.rank < P - 1:
+            band.set_halo_rows(top=False, rows=every[self.rank + 1, 0])
 
     # ----------------------------------------------------------------- hot path
     def flow_direction_accumulation(self, mode: int = 0):
@@ -140,18 +134,34 @@ class BandEngine:
             band.final(mode)
             self.launches += band.take_launches()
             return
+        # count modes: band-edge slots carry a mark through the first resolve, so that the
+        # second one only has to visit the nodes downstream of the band edge
+        delta = hasattr(band, "resolve_delta") and band.supports_delta(mode)
+        if delta:
+            band.mark_edges(mode)
         band.resolve(True)
         delivered, link = band.band_tables(mode)
         P = self.world
-        # (P*2, cols): concatenation along dim 0 is the layout every backend accepts
-        all_d = torch.empty((P * 2, self.cols), dtype=delivered.dtype, device=delivered.device)
-        all_l = torch.empty((P * 2, self.cols), dtype=link.dtype, device=link.device)
-        dist.all_gather_into_tensor(all_d, delivered.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_l, link.contiguous(), group=self.group)
-        base, nxt = build_band_graph(all_d.view(P, 2, self.cols), all_l.view(P, 2, self.cols))
+        # (P*k, cols): concatenation along dim 0 is the layout every backend accepts
+        if delivered.dtype == torch.int64:
+            # counts: both tables travel in one collective
+            both = torch.cat([delivered, link.to(torch.int64)])  # [4, cols]
+            every = torch.empty((P * 4, self.cols), dtype=torch.int64, device=both.device)
+            dist.all_gather_into_tensor(every, both, group=self.group)
+            every = every.view(P, 4, self.cols)
+            all_d, all_l = every[:, :2], every[:, 2:]
+        else:
+            all_d = torch.empty((P * 2, self.cols), dtype=delivered.dtype, device=delivered.device)
+            all_l = torch.empty((P * 2, self.cols), dtype=link.dtype, device=link.device)
+            dist.all_gather_into_tensor(all_d, delivered.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(all_l, link.contiguous(), group=self.group)
+        base, nxt = build_band_graph(all_d.reshape(P, 2, self.cols), all_l.reshape(P, 2, self.cols))
         inflow = band.forest_resolve(base, nxt, mode).view(P, 2, self.cols)
-        band.add_inflow(inflow[self.rank, 0], inflow[self.rank, 1], mode)
-        band.resolve(False)
+        if delta:
+            band.resolve_delta(inflow[self.rank, 0], inflow[self.rank, 1], mode)
+        else:
+            band.add_inflow(inflow[self.rank, 0], inflow[self.rank, 1], mode)
+            band.resolve(False)
         band.final(mode)
         self.launches += band.take_launches()
 
@@ -197,6 +207,7 @@ class CudaBand:
         self.weight, self.wld, self.wnd = None, 0, None
         self._launches = 0
         self._tmp = None
+        self._mark = None
 
     # ---- pointers
     def _dem0(self):
@@ -293,12 +304,41 @@ class CudaBand:
                     self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
         self._launches += 1
 
+    MARK = 1 << 48  # band-edge mark in the u64 sums of the boundary graph (csrc/ht_acc.cu)
+
+    def supports_delta(self, mode):
+        return mode != self.N.MODE_WEIGHTED
+
+    def mark_edges(self, mode=0):
+        """After stage A: tag the slots of the band's first / last row (where flow from a
+        neighbour band can come in) so that the resolve leaves a mark on every node
+        downstream of them."""
+        base0 = self._ws_view(0, torch.int64)
+        if self._mark is None:
+            self._mark = torch.full((self.cols,), self.MARK, dtype=torch.int64, device=self.dev)
+        if self.htop:
+            base0.index_add_(0, self.idx_top, self._mark)
+        if self.hbot:
+            base0.index_add_(0, self.idx_bot, self._mark)
+
+    def resolve_delta(self, top, bot, mode=0):
+        """Second resolve of a sharded run, over the marked nodes only."""
+        top = top.contiguous() if self.htop else None
+        bot = bot.contiguous() if self.hbot else None
+        self.N.call("ht_acc_resolve_delta", self.rows, self.cols, mode,
+                    top.data_ptr() if top is not None else None,
+                    bot.data_ptr() if bot is not None else None,
+                    self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
+        self._launches += 2
+
     def band_tables(self, mode=0):
         """(delivered [2, cols], link [2, cols]) after resolve(want_roots=True)."""
         vd = self._vdtype(mode)
         inflow = self._ws_view(2, vd)       # aggB
         root = self._ws_view(7, torch.int32)  # rootB
         delivered = inflow[self.vfirst:self.vfirst + 2 * self.cols].view(2, self.cols).clone()
+        if vd == torch.int64:
+            delivered &= self.MARK - 1
         link = torch.stack([root[self.idx_top], root[self.idx_bot]]).to(torch.int64) - self.vfirst
         link = torch.where(link >= 0, link, torch.full_like(link, -1)).to(torch.int32)
         return delivered, link

@@ -126,6 +126,15 @@ int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t
                  void *ws, size_t ws_bytes, void *stream);
 int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roots, void *ws,
                    size_t ws_bytes, int *rounds_dev, void *stream);
+/* row-band sharding, count modes: after ht_acc_resolve on a graph whose band-edge
+ * slots carried a mark (1 << 48 added to their base0 entry), add the effect of the
+ * flows the neighbour bands deliver into the band's first / last row (imp_top /
+ * imp_bot: cols values each, or NULL) and clear the marks -- a resolve over the
+ * nodes downstream of the band edge instead of a second full one */
+int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
+                         const unsigned long long *imp_top,
+                         const unsigned long long *imp_bot, void *ws, size_t ws_bytes,
+                         void *stream);
 int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
                  int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
                  int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,

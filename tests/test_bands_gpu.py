@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ND = -32767.0
 
 
-def run_bands(dem, cuts, nodata, csx, csy, mode=0, weight=None):
+def run_bands(dem, cuts, nodata, csx, csy, mode=0, weight=None, delta=False):
     from hydrotools.cuda import distributed as HD
     total, cols = dem.shape
     P = len(cuts) - 1
@@ -36,6 +36,8 @@ def run_bands(dem, cuts, nodata, csx, csy, mode=0, weight=None):
     for band in bands:
         band.direction()
         band.local(mode)
+        if delta:
+            band.mark_edges(mode)
         band.resolve(True)
         tabs.append(band.band_tables(mode))
     all_d = torch.stack([t[0] for t in tabs])
@@ -44,40 +46,46 @@ def run_bands(dem, cuts, nodata, csx, csy, mode=0, weight=None):
     inflow = bands[0].forest_resolve(base, nxt, mode).view(P, 2, cols)
     outs = []
     for b, band in enumerate(bands):
-        band.add_inflow(inflow[b, 0], inflow[b, 1], mode)
-        band.resolve(False)
+        if delta:  # resolve over the nodes downstream of the band edge only
+            band.resolve_delta(inflow[b, 0], inflow[b, 1], mode)
+        else:      # second full resolve
+            band.add_inflow(inflow[b, 0], inflow[b, 1], mode)
+            band.resolve(False)
         band.final(mode)
         fd, fa = band.results()
         outs.append((fd.cpu().numpy(), fa.cpu().numpy()))
     return np.vstack([o[0] for o in outs]), np.vstack([o[1] for o in outs])
 
 
+@pytest.mark.parametrize("delta", [False, True])
 @pytest.mark.parametrize("cuts", [[0, 150, 300], [0, 64, 128, 300], [0, 2, 100, 101 + 64, 300],
-                                  [0, 37, 38 + 37, 200, 300]])
-def test_bands_equal_oracle(hc, cuts):
+                                  [0, 37, 38 + 37, 200, 300], [0, 129, 300]])
+def test_bands_equal_oracle(hc, cuts, delta):
     dem = oracle.synth_dem(42, 300, 333, with_nulls=True)
-    fd, fa = run_bands(dem, cuts, ND, 10.0, 10.0)
+    fd, fa = run_bands(dem, cuts, ND, 10.0, 10.0, delta=delta)
     efd, efa = oracle.rwatershed(dem, ND, 10.0, 10.0)
     np.testing.assert_array_equal(fd, efd)
     np.testing.assert_array_equal(fa, efa)
 
 
-def test_bands_long_rivers(hc):
+@pytest.mark.parametrize("delta", [False, True])
+def test_bands_long_rivers(hc, delta):
     """Rivers cross every band boundary; meanders re-enter bands."""
     dem = oracle.synth_dem(20261019, 1500, 1100)
     cuts = [0, 200, 500, 777, 1100, 1500]
-    fd, fa = run_bands(dem, cuts, None, 10.0, 10.0)
+    fd, fa = run_bands(dem, cuts, None, 10.0, 10.0, delta=delta)
     efd, efa = oracle.rwatershed(dem, None, 10.0, 10.0)
     np.testing.assert_array_equal(fd, efd)
     np.testing.assert_array_equal(fa, efa)
 
 
-def test_bands_upward_flow(hc):
+@pytest.mark.parametrize("delta", [False, True])
+def test_bands_upward_flow(hc, delta):
     """Flip the DEM so that water runs towards row 0: flow crosses band boundaries
     upwards (virtual slots of the band above)."""
     dem = np.ascontiguousarray(oracle.synth_dem(7, 400, 300, with_nulls=True)[::-1])
     assert oracle.check_conditioned(dem, ND) == (0, 0)
-    fd, fa = run_bands(dem, [0, 130, 270, 400], ND, 10.0, 10.0)
+    fd, fa = run_bands(dem, [0, 130, 270, 400], ND, 10.0, 10.0, delta=delta)
     efd, efa = oracle.rwatershed(dem, ND, 10.0, 10.0)
     np.testing.assert_array_equal(fd, efd)
     np.testing.assert_array_equal(fa, efa)

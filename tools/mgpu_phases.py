@@ -28,17 +28,18 @@ for it in range(10):
     eng.exchange_halos(2); mark("halo exchange")
     band.direction(); mark("d8")
     band.local(0); mark("stage A")
+    band.mark_edges(0); mark("mark band edges")
     band.resolve(True); mark("stage B (roots)")
     delivered, link = band.band_tables(0); mark("band tables")
     P = world
-    all_d = torch.empty((P * 2, cols), dtype=delivered.dtype, device=delivered.device)
-    all_l = torch.empty((P * 2, cols), dtype=link.dtype, device=link.device)
-    dist.all_gather_into_tensor(all_d, delivered.contiguous())
-    dist.all_gather_into_tensor(all_l, link.contiguous()); mark("all_gather x2")
-    base, nxt = HD.build_band_graph(all_d.view(P, 2, cols), all_l.view(P, 2, cols)); mark("build band graph")
+    both = torch.cat([delivered, link.to(torch.int64)])
+    every = torch.empty((P * 4, cols), dtype=torch.int64, device=both.device)
+    dist.all_gather_into_tensor(every, both)
+    every = every.view(P, 4, cols)
+    all_d, all_l = every[:, :2], every[:, 2:]; mark("all_gather")
+    base, nxt = HD.build_band_graph(all_d.reshape(P, 2, cols), all_l.reshape(P, 2, cols)); mark("build band graph")
     inflow = band.forest_resolve(base, nxt, 0).view(P, 2, cols); mark("band forest resolve")
-    band.add_inflow(inflow[rank, 0], inflow[rank, 1], 0); mark("add inflow")
-    band.resolve(False); mark("stage B again")
+    band.resolve_delta(inflow[rank, 0], inflow[rank, 1], 0); mark("stage B delta")
     band.final(0); mark("stage C")
     torch.cuda.synchronize()
     for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
