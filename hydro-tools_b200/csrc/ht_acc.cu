@@ -1007,6 +1007,61 @@ __global__ void marked_nodes_kernel(const unsigned long long *agg, const int32_t
     }
 }
 
+// Row-band sharding, count modes: the two tables a band publishes after its first
+// resolve, in one launch.  out[0 / 1][c] = flow delivered into column c of the edge
+// row of the band above / below (marks cleared); out[2 / 3][c] = for the band's own
+// first / last row cell c, the foreign cell the path entering there finally
+// reaches (side * cols + column, side 0 = band above), or -1.
+__global__ void band_tables_kernel(const unsigned long long *agg, const int32_t *root, int64_t rows,
+                                   int64_t cols, int tiles_x, int tiles_y, int64_t vfirst,
+                                   long long *out)
+{
+    const int last_ty = tiles_y - 1;
+    const int last_h = (int)(rows - (int64_t)last_ty * T);
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long mask = (1ull << MARK_SHIFT) - 1ull;
+        out[c] = (long long)(agg[vfirst + c] & mask);
+        out[cols + c] = (long long)(agg[vfirst + cols + c] & mask);
+        const int64_t tx = c / T, lx = c % T;
+        const int64_t top = tx * SLOTS + lx;
+        const int64_t bot = ((int64_t)last_ty * tiles_x + tx) * SLOTS + (last_h == 1 ? lx : T + lx);
+        const long long rt = (long long)root[top] - vfirst, rb = (long long)root[bot] - vfirst;
+        out[2 * cols + c] = rt >= 0 ? rt : -1;
+        out[3 * cols + c] = rb >= 0 ? rb : -1;
+    }
+}
+
+// Band-level forest from the all-gathered tables (every[b][0..3][c] as written by
+// band_tables_kernel): node (b, s, c) = cell c of band b's first (s = 0) / last
+// (s = 1) row; base = what the neighbour band delivers into it, next = the node its
+// path reaches in a neighbour band, or -1.
+__global__ void band_graph_kernel(const long long *every, int P, int64_t cols,
+                                  unsigned long long *base, int32_t *next)
+{
+    const int64_t n = (int64_t)P * 2 * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / (2 * cols));
+        const int s = (int)((i / cols) & 1);
+        const int64_t c = i % cols;
+        unsigned long long v = 0ull;
+        if (s == 0 && b > 0)
+            v = (unsigned long long)every[((int64_t)(b - 1) * 4 + 1) * cols + c]; // sent down by the band above
+        if (s == 1 && b < P - 1)
+            v = (unsigned long long)every[((int64_t)(b + 1) * 4 + 0) * cols + c]; // sent up by the band below
+        base[i] = v;
+        const long long L = every[((int64_t)b * 4 + 2 + s) * cols + c];
+        int32_t nx = -1;
+        if (L >= 0) {
+            const long long side = L / cols, c2 = L - side * cols;
+            nx = side == 0 ? (int32_t)(((int64_t)(b - 1) * 2 + 1) * cols + c2)  // last row of the band above
+                           : (int32_t)(((int64_t)(b + 1) * 2 + 0) * cols + c2); // first row of the band below
+        }
+        next[i] = nx;
+    }
+}
+
 struct Workspace {
     uint16_t *lacc;
     int64_t lacc_ld;
@@ -1267,6 +1322,34 @@ extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
                                               wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
                                               nullptr, nullptr, wk.aggB, nullptr, wk.flags, nullptr,
                                               st, 1);
+}
+
+extern "C" int ht_band_tables(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
+                              long long *out4, void *stream)
+{
+    if (rows <= 0 || cols <= 0 || !out4)
+        return HT_ERR_ARG;
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    if (rc)
+        return rc;
+    band_tables_kernel<<<ht::cdiv(cols, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned long long *)wk.aggB, wk.rootB, rows, cols, ht::cdiv(cols, T),
+        ht::cdiv(rows, T), wk.nslots - 2 * cols, out4);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
+}
+
+extern "C" int ht_band_graph(const long long *every, int bands, int64_t cols,
+                             unsigned long long *base, int32_t *next, void *stream)
+{
+    if (!every || !base || !next || bands <= 0 || cols <= 0 ||
+        (int64_t)bands * 2 * cols >= INT32_MAX)
+        return HT_ERR_ARG;
+    band_graph_kernel<<<ht::cdiv((int64_t)bands * 2 * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+        every, bands, cols, base, next);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
 }
 
 // Byte offsets (from the workspace pointer) of the boundary-graph arrays, for the

@@ -53,6 +53,8 @@ SIGNATURES = {
                      _f32, _p, C.c_size_t, _p],
     "ht_acc_resolve": [_i64, _i64, _int, _int, _p, C.c_size_t, _p, _p],
     "ht_acc_resolve_delta": [_i64, _i64, _int, _p, _p, _p, C.c_size_t, _p],
+    "ht_band_tables": [_i64, _i64, _p, C.c_size_t, _p, _p],
+    "ht_band_graph": [_p, _int, _i64, _p, _p, _p],
     "ht_acc_final": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _i64, _int,
                      _f32, _p, _i64, _p, _i64, _p, C.c_size_t, _p],
     "ht_acc_f64": [_p, _i64, _i64, _i64, _int, _p, _i64, _int, _f32, _p, _i64, _p, _i64,

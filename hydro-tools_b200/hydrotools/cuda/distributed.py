@@ -140,22 +140,29 @@ class BandEngine:
         if delta:
             band.mark_edges(mode)
         band.resolve(True)
-        delivered, link = band.band_tables(mode)
         P = self.world
-        # (P*k, cols): concatenation along dim 0 is the layout every backend accepts
-        if delivered.dtype == torch.int64:
-            # counts: both tables travel in one collective
-            both = torch.cat([delivered, link.to(torch.int64)])  # [4, cols]
+        if delta and hasattr(band, "band_tables4"):
+            # counts on the device: both tables from one kernel, one collective, and the
+            # band-level forest from one kernel
+            both = band.band_tables4()  # [4, cols] int64
             every = torch.empty((P * 4, self.cols), dtype=torch.int64, device=both.device)
             dist.all_gather_into_tensor(every, both, group=self.group)
-            every = every.view(P, 4, self.cols)
-            all_d, all_l = every[:, :2], every[:, 2:]
+            base, nxt = band.band_graph(every, P)
         else:
-            all_d = torch.empty((P * 2, self.cols), dtype=delivered.dtype, device=delivered.device)
-            all_l = torch.empty((P * 2, self.cols), dtype=link.dtype, device=link.device)
-            dist.all_gather_into_tensor(all_d, delivered.contiguous(), group=self.group)
-            dist.all_gather_into_tensor(all_l, link.contiguous(), group=self.group)
-        base, nxt = build_band_graph(all_d.reshape(P, 2, self.cols), all_l.reshape(P, 2, self.cols))
+            delivered, link = band.band_tables(mode)
+            # (P*k, cols): concatenation along dim 0 is the layout every backend accepts
+            if delivered.dtype == torch.int64:
+                both = torch.cat([delivered, link.to(torch.int64)])  # [4, cols]
+                every = torch.empty((P * 4, self.cols), dtype=torch.int64, device=both.device)
+                dist.all_gather_into_tensor(every, both, group=self.group)
+                every = every.view(P, 4, self.cols)
+                all_d, all_l = every[:, :2], every[:, 2:]
+            else:
+                all_d = torch.empty((P * 2, self.cols), dtype=delivered.dtype, device=delivered.device)
+                all_l = torch.empty((P * 2, self.cols), dtype=link.dtype, device=link.device)
+                dist.all_gather_into_tensor(all_d, delivered.contiguous(), group=self.group)
+                dist.all_gather_into_tensor(all_l, link.contiguous(), group=self.group)
+            base, nxt = build_band_graph(all_d.reshape(P, 2, self.cols), all_l.reshape(P, 2, self.cols))
         inflow = band.forest_resolve(base, nxt, mode).view(P, 2, self.cols)
         if delta:
             band.resolve_delta(inflow[self.rank, 0], inflow[self.rank, 1], mode)
@@ -330,6 +337,25 @@ class CudaBand:
                     bot.data_ptr() if bot is not None else None,
                     self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
         self._launches += 2
+
+    def band_tables4(self):
+        """Count modes: [delivered up, delivered down, link top, link bottom] x cols (int64),
+        one kernel."""
+        out = torch.empty((4, self.cols), dtype=torch.int64, device=self.dev)
+        self.N.call("ht_band_tables", self.rows, self.cols, self.ws.data_ptr(), self.ws.numel(),
+                    out.data_ptr(), self.D.stream_ptr())
+        self._launches += 1
+        return out
+
+    def band_graph(self, every, bands):
+        """Band-level forest (base u64 as int64, next int32) from the all-gathered tables."""
+        n = bands * 2 * self.cols
+        base = torch.empty(n, dtype=torch.int64, device=self.dev)
+        nxt = torch.empty(n, dtype=torch.int32, device=self.dev)
+        self.N.call("ht_band_graph", every.data_ptr(), bands, self.cols, base.data_ptr(),
+                    nxt.data_ptr(), self.D.stream_ptr())
+        self._launches += 1
+        return base, nxt
 
     def band_tables(self, mode=0):
         """(delivered [2, cols], link [2, cols]) after resolve(want_roots=True)."""

@@ -135,6 +135,17 @@ int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
                          const unsigned long long *imp_top,
                          const unsigned long long *imp_bot, void *ws, size_t ws_bytes,
                          void *stream);
+/* row-band sharding, count modes, after ht_acc_resolve(want_roots = 1): the tables a
+ * band publishes, out4[4][cols] (int64): [0] / [1] flow delivered into column c of
+ * the edge row of the band above / below, [2] / [3] for the band's own first / last
+ * row cell c the foreign cell its path finally reaches (side * cols + column, side
+ * 0 = band above) or -1 */
+int ht_band_tables(int64_t rows, int64_t cols, void *ws, size_t ws_bytes, long long *out4,
+                   void *stream);
+/* the band-level forest from the all-gathered tables every[bands][4][cols]:
+ * base[bands][2][cols], next[bands][2][cols] for ht_forest_resolve */
+int ht_band_graph(const long long *every, int bands, int64_t cols, unsigned long long *base,
+                  int32_t *next, void *stream);
 int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
                  int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
                  int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,

@@ -43,6 +43,15 @@ def run_bands(dem, cuts, nodata, csx, csy, mode=0, weight=None, delta=False):
     all_d = torch.stack([t[0] for t in tabs])
     all_l = torch.stack([t[1] for t in tabs])
     base, nxt = HD.build_band_graph(all_d, all_l)
+    if delta:
+        # the fused kernels BandEngine uses in count modes give the same tables / forest
+        every = torch.cat([band.band_tables4() for band in bands])
+        for b in range(P):
+            assert torch.equal(every[4 * b:4 * b + 2], tabs[b][0])
+            assert torch.equal(every[4 * b + 2:4 * b + 4], tabs[b][1].to(torch.int64))
+        base2, nxt2 = bands[0].band_graph(every, P)
+        assert torch.equal(base2, base) and torch.equal(nxt2, nxt)
+        base, nxt = base2, nxt2
     inflow = bands[0].forest_resolve(base, nxt, mode).view(P, 2, cols)
     outs = []
     for b, band in enumerate(bands):
