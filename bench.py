@@ -24,9 +24,10 @@ import sys
 import threading
 import time
 
-# NCCL's version banner goes to stdout; the contract is ONE JSON line there
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION and WARN; the contract is
+# ONE JSON line there.  INFO / TRACE, if somebody asks for them, are left alone.
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
