@@ -650,7 +650,7 @@ constexpr int SMF_BAR = SMF_LUT + 64;
 constexpr int SMF_TOTAL = SMF_BAR + 16;
 
 template <int WMODE>
-__global__ void __launch_bounds__(THREADS, 5)
+__global__ void __launch_bounds__(THREADS, 6)
 acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
