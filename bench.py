@@ -291,11 +291,13 @@ def run_product(args):
     path_roofline = {"algorithmic_bytes_per_cell": 14, "achieved": path_gbs, "peak": peak,
                      "unit": "GB/s", "frac": path_gbs / peak}
 
-    stencil = None
     cpu = None
+    # configs[2]: fused slope + aspect + TRI on 32768^2; with N > 1 the same raster in N
+    # row bands (strong scaling), halo rows exchanged inside the timed region
+    del engine
+    torch.cuda.empty_cache()
+    stencil = terrain_roofline(peak) if world == 1 else terrain_bands(peak, rank, world, barrier, dev)
     if rank == 0:
-        if world == 1:
-            stencil = terrain_roofline(peak)
         g, dt = oracle_sample_gcells(2500, COLS, total_rows)
         cpu = {"value": g, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first 2500 rows x {COLS} cols of the same DEM, oracle/rwatershed.c "
@@ -356,6 +358,37 @@ def terrain_roofline(peak):
     return {"kernel": "terrain_kernel (fused slope+aspect+TRI)", "workload": f"{n}x{n} fp32",
             "ms": ms, "gcells_s": n * n / (ms * 1e-3) / 1e9, "achieved": gbs, "peak": peak,
             "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_cell": 16}
+
+
+def terrain_bands(peak, rank, world, barrier, dev):
+    import torch
+    import torch.distributed as dist
+    from hydrotools.cuda import distributed as HD
+    n = TERRAIN_N
+    rows = n // world
+    eng = HD.BandEngine(rank, world, rows, n, rows * world, CSX, CSY, nodata=None)
+    eng.generate_synthetic(SEED)
+    for _ in range(3):
+        out = eng.terrain()
+    del out
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        out = eng.terrain()
+        del out
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    cells = rows * world * n
+    gbs_per_gpu = rows * n * 16 / (ms * 1e-3) / 1e9
+    return {"kernel": "terrain_kernel (fused slope+aspect+TRI)", "workload": f"{rows * world}x{n} fp32 in "
+            f"{world} row bands, 1 halo row exchanged per shared side and step", "ms": ms,
+            "gcells_s": cells / (ms * 1e-3) / 1e9, "achieved": gbs_per_gpu, "peak": peak,
+            "unit": "GB/s per GPU", "frac": gbs_per_gpu / peak, "algorithmic_bytes_per_cell": 16,
+            "scaling": "strong"}
 
 
 def main():
