@@ -7,27 +7,23 @@
 //     acc(c) = w(c) + sum of acc(u) over cells u whose receiver is c.
 //
 // Three stages, all on the device (Barnes-style tile decomposition):
-//  A  acc_tile_kernel<LOCAL>: per 64x64 tile held in shared memory, count
-//     remaining donors per cell and propagate in topological order: a thread
-//     starts at a source, hands its value on with one shared-memory atomic, and
-//     keeps walking for as long as it was the last donor to arrive.  Flow that
+//  A  acc_local_cnt_kernel / acc_f64_kernel<false>: per 64x64 tile held in shared
+//     memory, subtree sums over the tile's forest by pointer doubling.  Flow that
 //     leaves the tile is added to the boundary graph (`base`), and every entry
 //     cell records where its path leaves the tile (`next`).
 //  B  coarse_resolve_kernel: the boundary graph (one slot per tile-perimeter
 //     cell) is a forest; subtree sums by pointer doubling, iterated inside one
-//     cooperative launch until no pointer changes.
-//  C  acc_tile_kernel<FINAL>: stage A again with the resolved inflow added at
-//     the entry cells; writes the accumulation (fp64, exact integers for counts)
-//     and the final GRASS direction codes.
-// Counts are carried as u64; weighted sums as fp64 gathered in a fixed
-// neighbour order (no floating-point atomics inside a tile => reproducible).
+//     cooperative launch until no node is active.
+//  C  acc_final_cnt_kernel (counts: tile-local counts + the resolved inflow walked
+//     along the entry paths) / acc_f64_kernel<true> (weights: stage A again with
+//     the inflow arriving at the entry cells); writes the accumulation (fp64,
+//     exact integers for counts) and the final GRASS direction codes.
+// Counts are carried as u64 across tiles; weighted sums as fp64.
 // Algorithmic traffic: 1 B/cell read + 8 B/cell written (+4 B/cell weights).
-#include <cooperative_groups.h>
 #include <type_traits>
 
 #include "ht_common.cuh"
 
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -41,13 +37,8 @@ constexpr int CPT = T * T / THREADS; // cells per thread
 constexpr int SLOTS = 4 * T;     // boundary-graph slots per tile
 constexpr int32_t TERMINAL = -1;
 
-// dynamic shared memory layout of acc_tile_kernel
+// the ring tile (TMA destination) comes first in every kernel's dynamic shared memory
 constexpr int SM_EFF = (RH * RP + 127) / 128 * 128;
-constexpr int SM_VAL = 2 * SM_EFF;
-constexpr int SM_PEND = SM_VAL + T * T * 8;
-constexpr int SM_DON = SM_PEND + T * T;
-constexpr int SM_BAR = SM_DON + T * T;
-constexpr int SM_TOTAL = SM_BAR + 16;
 
 enum { W_ONE = 0, W_TAINT = 1, W_F32 = 2 };
 
@@ -83,30 +74,6 @@ __device__ __forceinline__ int win2code(int k) { return (int)((0x765804123ULL >>
 // r.watershed neighbour order S,N,W,E,NE,SW,SE,NW as window cells
 __device__ __forceinline__ int ct2win(int ct) { return (0x08625317u >> (4 * ct)) & 0xF; }
 
-// slot of the perimeter cell (lr, gc) [band-local row, column]
-__device__ __forceinline__ int64_t slot_of(const AccArgs &p, int64_t lr, int64_t gc)
-{
-    const int ty = (int)(lr / T), tx = (int)(gc / T);
-    const int ly = (int)(lr - (int64_t)ty * T), lx = (int)(gc - (int64_t)tx * T);
-    const int h = (int)min((int64_t)T, p.rows - (int64_t)ty * T);
-    const int wd = (int)min((int64_t)T, p.cols - (int64_t)tx * T);
-    int k;
-    if (ly == 0) k = lx;
-    else if (ly == h - 1) k = T + lx;
-    else if (lx == 0) k = 2 * T + ly;
-    else k = 3 * T + ly; // lx == wd - 1
-    (void)wd;
-    return ((int64_t)ty * p.tiles_x + tx) * SLOTS + k;
-}
-
-// virtual slots for the cells of the neighbouring bands that this band drains into
-__device__ __forceinline__ int64_t vslot_of(const AccArgs &p, bool bottom, int64_t gc)
-{
-    return (int64_t)p.tiles_x * p.tiles_y * SLOTS + (bottom ? p.cols : 0) + gc;
-}
-
-__device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
-
 // perimeter slot k of a th x tw tile -> (ly, lx); false for duplicates / unused
 __device__ __forceinline__ bool perimeter_cell(int k, int th, int tw, int &ly, int &lx)
 {
@@ -119,296 +86,9 @@ __device__ __forceinline__ bool perimeter_cell(int k, int th, int tw, int &ly, i
 
 static_assert(SLOTS == THREADS, "one perimeter slot per thread");
 
-// Every thread of the CTA calls this once (convergent).  Entry cells record their
-// successor and are appended to the list of boundary-graph nodes, one global
-// atomic per warp.
-__device__ __forceinline__ void publish_entry(const AccArgs &p, bool entry, int64_t slot, int32_t nxt)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, entry);
-    if (!m)
-        return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader)
-        base = atomicAdd(p.nlist, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (entry) {
-        p.list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)slot;
-        p.next[slot] = nxt;
-    }
-}
-
 template <typename V> __device__ __forceinline__ void atomic_add_v(V *p, V v);
 template <> __device__ __forceinline__ void atomic_add_v<unsigned long long>(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 template <> __device__ __forceinline__ void atomic_add_v<double>(double *p, double v) { atomicAdd(p, v); }
-
-template <typename V, int WMODE, bool FINAL>
-__global__ void __launch_bounds__(THREADS, 5)
-acc_tile_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint8_t *pk = smem_raw;                                       // packed bytes, tile + ring
-    uint8_t *eff = smem_raw + SM_EFF;                             // effective link 0..8
-    V *val = reinterpret_cast<V *>(smem_raw + SM_VAL);
-    uint32_t *pend32 = reinterpret_cast<uint32_t *>(smem_raw + SM_PEND); // donors still to arrive
-    uint8_t *don = smem_raw + SM_DON;                             // all in-tile donors (bit mask)
-    // the mbarrier sits behind whichever value layout this instantiation uses
-    uint64_t &bar = *reinterpret_cast<uint64_t *>(
-        smem_raw + (std::is_same<V, double>::value ? SM_BAR : SM_VAL + T * T * (FINAL ? 8 : 4)));
-
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
-
-    if (tid == 0) {
-        ht::mbar_init(&bar, 1);
-        ht::fence_mbar_init();
-        ht::mbar_expect_tx(&bar, RH * RP);
-        ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
-    }
-    __syncthreads();
-    ht::mbar_wait(&bar, 0);
-
-    // a ring-tile cell is usable if it lies in this band (or its halo rows), inside
-    // the raster, and is not NULL
-    auto valid = [&](int yy, int xx) -> bool {
-        const int64_t lr = y0 - 1 + yy, gc = x0 - XO + xx;
-        if (gc < 0 || gc >= p.cols || lr < -(int64_t)p.halo_top || lr >= p.rows + p.halo_bot)
-            return false;
-        return !(pk[yy * RP + xx] & HT_DIR_NULL);
-    };
-
-    // ---- S1: effective link of every cell of tile + ring
-    for (int i = tid; i < RH * RH; i += THREADS) {
-        const int yy = i / RH, xx = i - yy * RH + XO - 1;
-        int link = 0;
-        if (valid(yy, xx)) {
-            const uint8_t b = pk[yy * RP + xx];
-            const int code = b & HT_DIR_CODE;
-            if (!(b & (HT_DIR_NEG | HT_DIR_EDGE)) && code >= 1 && code <= 8) {
-                const int ny = yy + code_dr(code), nx = xx + code_dc(code);
-                if (ny >= 0 && ny < RH && nx >= XO - 1 && nx <= XO + T && valid(ny, nx))
-                    link = code;
-            }
-        }
-        eff[yy * RP + xx] = (uint8_t)link;
-    }
-    __syncthreads();
-
-    // ---- S2: donor counts / masks, initial values
-    // counts: one 32-bit word per cell = [donors still to arrive : 4 | low part : 28]
-    // plus (stage C only, where inflow can exceed 2^24) a high word; a value is
-    // hi * 2^24 + lo with lo allowed to run up to 9 * 2^24 unnormalised.
-    constexpr bool CNT = !std::is_same<V, double>::value;
-    uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SM_VAL);
-    uint32_t *hi32 = lo32 + T * T;
-    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
-    unsigned src_mask = 0; // which of my CPT cells are sources
-#pragma unroll 4
-    for (int i = 0; i < CPT; i++) {
-        const int c = tid + i * THREADS;
-        const int ly = c / T, lx = c - ly * T;
-        const int yy = ly + 1, xx = lx + XO;
-        unsigned m_in = 0;
-        const bool ok = ly < th && lx < tw && valid(yy, xx);
-        V v = 0;
-        if (ok) {
-#pragma unroll
-            for (int kk = 0; kk < 9; kk++) {
-                if (kk == 4)
-                    continue;
-                const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
-                const bool pts = eff[ny * RP + nx] == win2code(8 - kk);
-                const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
-                if (pts && in_tile)
-                    m_in |= 1u << (kk < 4 ? kk : kk - 1);
-            }
-            if (WMODE == W_ONE)
-                v = 1;
-            else if (WMODE == W_TAINT)
-                v = (pk[yy * RP + xx] & HT_DIR_TAINT) ? 1 : 0;
-            else {
-                const float wv = p.w[(y0 + ly) * p.w_ld + x0 + lx];
-                v = ((p.has_wnd && wv == p.wnd) || wv != wv) ? (V)0 : (V)wv;
-            }
-            if (FINAL && (ly == 0 || ly == th - 1 || lx == 0 || lx == tw - 1))
-                v += reinterpret_cast<const V *>(p.inflow)[slot_of(p, y0 + ly, x0 + lx)];
-            if (m_in == 0)
-                src_mask |= 1u << i;
-        }
-        if constexpr (CNT) {
-            const unsigned long long u = (unsigned long long)v;
-            lo32[c] = ((unsigned)__popc(m_in) << 28) | (unsigned)(u & 0xFFFFFFu);
-            if (FINAL)
-                hi32[c] = (unsigned)(u >> 24);
-        }
-        else {
-            don[c] = (uint8_t)m_in;
-            reinterpret_cast<uint8_t *>(pend32)[c] = (uint8_t)m_in;
-            val[c] = v;
-        }
-    }
-    __syncthreads();
-
-    // ---- S3: topological propagation (chain following)
-    for (int i = 0; i < CPT; i++) {
-        if (!((src_mask >> i) & 1u))
-            continue;
-        int cur = tid + i * THREADS;
-        V v;
-        if constexpr (CNT)
-            v = (V)(lo32[cur] & 0x0FFFFFFFu) + (FINAL ? ((V)hi32[cur] << 24) : (V)0);
-        else
-            v = val[cur];
-        for (;;) {
-            const int ly = cur / T, lx = cur - ly * T;
-            const int link = eff[(ly + 1) * RP + lx + XO];
-            if (!link)
-                break;
-            const int dr = code_dr(link), dc = code_dc(link);
-            const int ny = ly + dr, nx = lx + dc;
-            if (ny < 0 || ny >= th || nx < 0 || nx >= tw) {
-                if (!FINAL) { // flow leaves the tile: feed the boundary graph
-                    const int64_t lr = y0 + ny, gc = x0 + nx;
-                    const int64_t s = lr < 0 ? vslot_of(p, false, gc)
-                                    : lr >= p.rows ? vslot_of(p, true, gc)
-                                                   : slot_of(p, lr, gc);
-                    atomic_add_v(reinterpret_cast<V *>(p.base) + s, v);
-                }
-                break;
-            }
-            const int rc = ny * T + nx;
-            if constexpr (CNT) {
-                // one atomic hands the value on and counts the arrival
-                const unsigned long long u = (unsigned long long)v;
-                const unsigned v_lo = (unsigned)(u & 0xFFFFFFu), v_hi = (unsigned)(u >> 24);
-                if (FINAL && v_hi) {
-                    atomicAdd(&hi32[rc], v_hi);
-                    __threadfence_block();
-                }
-                const unsigned old = atomicAdd(&lo32[rc], v_lo + 0xF0000000u);
-                if ((old >> 28) != 1u)
-                    break; // other donors still to come; the last one continues
-                v = (V)((old & 0x0FFFFFFFu) + v_lo);
-                if (FINAL)
-                    v += (V)hi32[rc] << 24;
-            }
-            else {
-                const int kme = (1 - dr) * 3 + (1 - dc); // me, seen from the receiver
-                const unsigned bit = 1u << (kme < 4 ? kme : kme - 1);
-                const int sh = 8 * (rc & 3);
-                fence_acq_rel_cta();
-                const unsigned old = atomicAnd(&pend32[rc >> 2], ~(bit << sh));
-                if (((old >> sh) & 0xFFu) != bit)
-                    break;
-                fence_acq_rel_cta();
-                // gather in fixed neighbour order: own weight + all donors
-                V sum = val[rc];
-                unsigned m = don[rc];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int kk = b < 4 ? b : b + 1;
-                    sum += val[rc + (kk / 3 - 1) * T + (kk % 3 - 1)];
-                }
-                val[rc] = sum;
-                v = sum;
-            }
-            cur = rc;
-        }
-    }
-    __syncthreads();
-
-    if (!FINAL) {
-        // ---- S4a: where does the path of each entry cell leave the tile?
-        {
-            const int k = tid; // one perimeter slot per thread
-            int ly, lx;
-            bool entry = false;
-            int32_t nxt = TERMINAL;
-            int64_t slot = 0;
-            if (perimeter_cell(k, th, tw, ly, lx) && valid(ly + 1, lx + XO)) {
-                const int yy = ly + 1, xx = lx + XO;
-#pragma unroll
-                for (int kk = 0; kk < 9; kk++) {
-                    if (kk == 4)
-                        continue;
-                    const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
-                    const bool in_tile = ny >= 1 && ny <= th && nx >= XO && nx < XO + tw;
-                    entry |= !in_tile && eff[ny * RP + nx] == win2code(8 - kk);
-                }
-                if (entry) {
-                    slot = slot_of(p, y0 + ly, x0 + lx);
-                    int cy = ly, cx = lx;
-                    for (;;) {
-                        const int link = eff[(cy + 1) * RP + cx + XO];
-                        if (!link)
-                            break;
-                        const int ny = cy + code_dr(link), nx = cx + code_dc(link);
-                        if (ny < 0 || ny >= th || nx < 0 || nx >= tw) {
-                            const int64_t lr = y0 + ny, gc = x0 + nx;
-                            nxt = (int32_t)(lr < 0 ? vslot_of(p, false, gc)
-                                          : lr >= p.rows ? vslot_of(p, true, gc)
-                                                         : slot_of(p, lr, gc));
-                            break;
-                        }
-                        cy = ny;
-                        cx = nx;
-                    }
-                }
-            }
-            publish_entry(p, entry, slot, nxt);
-        }
-    }
-    else {
-        // ---- S4b: write accumulation and final direction codes, row-coalesced
-        for (int c = tid; c < T * T; c += THREADS) {
-            const int ly = c / T, lx = c - ly * T;
-            if (ly >= th || lx >= tw)
-                continue;
-            const int yy = ly + 1, xx = lx + XO;
-            const uint8_t b = pk[yy * RP + xx];
-            const bool null = b & HT_DIR_NULL;
-            double a;
-            if constexpr (CNT)
-                a = (double)((unsigned long long)(lo32[c] & 0x0FFFFFFFu) +
-                             ((unsigned long long)hi32[c] << 24));
-            else
-                a = (double)val[c];
-            if (p.acc)
-                p.acc[(y0 + ly) * p.acc_ld + x0 + lx] = null ? __longlong_as_double(0x7ff8000000000000LL) : a;
-            if (p.dir_out) {
-                int code = b & HT_DIR_CODE;
-                int out;
-                if (null)
-                    out = -128;
-                else if (b & HT_DIR_NEG)
-                    out = -code;
-                else if ((b & HT_DIR_EDGE) && a >= 60.0) {
-                    // rule R5: an edge cell that is a swale (|acc| >= 60) gets its
-                    // outward code back: first neighbour outside the raster / NULL
-                    // in the order S,N,W,E,NE,SW,SE,NW
-                    out = 0;
-#pragma unroll
-                    for (int ct = 7; ct >= 0; ct--) {
-                        const int kk = ct2win(ct);
-                        const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
-                        const int64_t gr = p.row0 + y0 - 1 + ny, gc = x0 - XO + nx;
-                        const bool outside = gr < 0 || gr >= p.total_rows || gc < 0 || gc >= p.cols;
-                        if (outside || (pk[ny * RP + nx] & HT_DIR_NULL))
-                            out = -win2code(kk);
-                    }
-                    if (out == 0)
-                        out = code; // not an edge after all (foreign packed grid)
-                }
-                else
-                    out = code;
-                p.dir_out[(y0 + ly) * p.dir_ld + x0 + lx] = (int8_t)out;
-            }
-        }
-    }
-}
 
 // ===========================================================================
 // Count modes (cell counts, taint counts): lean integer kernels.
@@ -636,6 +316,198 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             if (ly0 + 4 * k < th)
                 *dst = (uint16_t)(((own >> k) & 1u) + arr[tid + k * THREADS]);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Weighted mode (fp32 weights, fp64 sums): the same pointer doubling with double
+// sums and shared fp64 atomics.  Stage C is stage A again with the resolved inflow
+// of the entry slots arriving as initial sums -- no tile-local hand-over (it would
+// cost 8 B per cell), no walkers.  The order of the atomic adds is not fixed, so
+// results agree from run to run to ~1e-15 relative, far inside the 1e-5 contract.
+// ---------------------------------------------------------------------------
+constexpr int SMD_PTR = SM_EFF;                  // uint16[T*T] pointer entries
+constexpr int SMD_ARR = SMD_PTR + T * T * 2;     // double[T*T] sums that arrived at a cell
+constexpr int SMD_LUT = SMD_ARR + T * T * 8;     // uint32[16] code -> pointer step | active
+constexpr int SMD_BAR = SMD_LUT + 64;
+constexpr int SMD_TOTAL = SMD_BAR + 32;
+static_assert(SMD_ARR % 8 == 0, "fp64 array alignment");
+
+template <bool FINAL>
+__global__ void __launch_bounds__(THREADS, 2)
+acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *pk = smem_raw;
+    unsigned char *ptrb = smem_raw + SMD_PTR;   // uint16[T*T]
+    unsigned char *arrb = smem_raw + SMD_ARR;   // double[T*T]
+    uint16_t *ptr16 = reinterpret_cast<uint16_t *>(ptrb);
+    double *arr = reinterpret_cast<double *>(arrb);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMD_LUT);
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMD_BAR);
+    int *ctl = reinterpret_cast<int *>(smem_raw + SMD_BAR + 8); // [0] entries of the tile, [1] their place in the list
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
+    if (tid == 0) {
+        ctl[0] = 0;
+        ht::mbar_init(&bar, 1);
+        ht::fence_mbar_init();
+        ht::mbar_expect_tx(&bar, RH * RP);
+        ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
+    }
+    if (tid < 16) // added to 2 * (cell index); codes 0, 9..15 never link
+        lut[tid] = link_offset_of(tid) ? (unsigned)(link_offset_of(tid) * 2) + J_ACTIVE : 0u;
+    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
+    // thread -> cells tid + 256 k: one column, every 4th row.  A warp covers 32
+    // consecutive cells of a row in every step (conflict-free own accesses).
+    const int lx = tid & (T - 1), ly0 = tid >> 6;
+#pragma unroll
+    for (int k = 0; k < CPT; k++)
+        arr[tid + k * THREADS] = 0.0;
+    __syncthreads();
+    if (FINAL) { // resolved inflow of the tile's entry slots arrives like any other donor's sum
+        int ly, plx;
+        if (perimeter_cell(tid, th, tw, ly, plx))
+            arr[ly * T + plx] = reinterpret_cast<const double *>(p.inflow)[(int64_t)tile * SLOTS + tid];
+    }
+    ht::mbar_wait(&bar, 0);
+
+    // ---- per cell: low = pointer entry, a = sum to hand on, own = the cell's own value
+    unsigned low[CPT];
+    double a[CPT];
+    float own[CPT]; // the cells' own weights (0 where NULL / nodata)
+    {
+        // codes that do not link from this column; bit 15: outside the raster; bit 0: code 0
+        const unsigned cm = (lx == 0 ? EX_W : 0u) | (lx == tw - 1 ? EX_E : 0u) | (lx >= tw ? 0xFFFFu : 0u) | 1u;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int ly = ly0 + 4 * k;
+            const unsigned b = pk[(ly + 1) * RP + XO + lx];
+            const unsigned ex = cm | (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u) | (ly >= th ? 0xFFFFu : 0u);
+            const unsigned code = b & HT_DIR_CODE;
+            // no link: a stop flag, or the receiver is outside the tile / the raster
+            const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
+            const bool valid = !(b & HT_DIR_NULL) && !(ex >> 15);
+            float wv = 0.0f;
+            if (valid) {
+                wv = p.w[(y0 + ly) * p.w_ld + x0 + lx];
+                if ((p.has_wnd && wv == p.wnd) || wv != wv)
+                    wv = 0.0f;
+            }
+            own[k] = wv;
+            low[k] = 2u * (unsigned)(tid + k * THREADS) + (stop ? 0u : lut[code]);
+            ptr16[tid + k * THREADS] = (uint16_t)low[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CPT; k++)
+        a[k] = (double)own[k] + arr[tid + k * THREADS]; // arr: the inflow (FINAL) or 0
+    __syncthreads();
+
+    // ---- pointer doubling.  Only the pointer entries live in shared memory (they are
+    // what other cells read); sums arrive in arr[] and are snapshot into registers.
+    for (int round = 0; round < MAX_ROUNDS; round++) {
+        unsigned was = 0; // cells that were active in this round
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            if (low[k] & J_ACTIVE) {
+                const unsigned t2 = low[k] & J_PTR; // 2 * (cell 2^k steps downstream)
+                const unsigned wt = *reinterpret_cast<const uint16_t *>(ptrb + t2);
+                if (a[k] != 0.0)
+                    atomicAdd(reinterpret_cast<double *>(arrb + 4 * t2), a[k]);
+                // t still active: its pointer is 2^(k+1) steps from me; else I am done and
+                // keep the root of the path (t's pointer; a root points at itself)
+                low[k] = wt;
+                was |= 1u << k;
+            }
+        }
+        __syncthreads();
+        bool still = false;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            if ((was >> k) & 1u) {
+                ptr16[tid + k * THREADS] = (uint16_t)low[k];
+                if (low[k] & J_ACTIVE) {
+                    a[k] = (double)own[k] + arr[tid + k * THREADS];
+                    still = true;
+                }
+            }
+        }
+        if (!__syncthreads_or(still))
+            break;
+    }
+
+    if (FINAL) {
+        // ---- outputs: fp64 sums, NaN where NULL
+        if (p.acc && lx < tw) {
+            double *dst = p.acc + (y0 + ly0) * p.acc_ld + x0 + lx;
+#pragma unroll
+            for (int k = 0; k < CPT; k++, dst += 4 * p.acc_ld) {
+                const int ly = ly0 + 4 * k;
+                if (ly >= th)
+                    break;
+                const bool null = pk[(ly + 1) * RP + XO + lx] & HT_DIR_NULL;
+                *dst = null ? __longlong_as_double(0x7ff8000000000000LL)
+                            : (double)own[k] + arr[tid + k * THREADS];
+            }
+        }
+        return;
+    }
+
+    // ---- boundary graph.  thread -> one perimeter slot
+    {
+        int ly = 0, plx = 0;
+        const bool per = perimeter_cell(tid, th, tw, ly, plx);
+        const unsigned b = per ? pk[(ly + 1) * RP + plx + XO] : (unsigned)HT_DIR_NULL;
+        // flow that leaves the tile through this cell
+        if (per && leaves_tile(b, ly, plx, th, tw)) {
+            float self = p.w[(y0 + ly) * p.w_ld + x0 + plx];
+            if ((p.has_wnd && self == p.wnd) || self != self)
+                self = 0.0f;
+            const double val = (double)self + arr[ly * T + plx];
+            if (val != 0.0)
+                atomicAdd(reinterpret_cast<double *>(p.base) +
+                              exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE)), val);
+        }
+        // entry cell: a cell outside the tile drains into it
+        bool entry = false;
+        if (per && !(b & HT_DIR_NULL)) {
+            const int yy = ly + 1, xx = plx + XO;
+#pragma unroll
+            for (int kk = 0; kk < 9; kk++) {
+                if (kk == 4)
+                    continue;
+                const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
+                if (ny >= 1 && ny <= th && nx >= XO && nx < XO + tw)
+                    continue; // inside the tile
+                const unsigned u = pk[ny * RP + nx]; // outside the raster: TMA filled 0
+                entry |= !(u & FLAGS_STOP) && (u & HT_DIR_CODE) == (unsigned)win2code(8 - kk);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, entry);
+        int at = 0;
+        if (lane == 0 && m)
+            at = atomicAdd(&ctl[0], __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+        __syncthreads();
+        if (tid == 0 && ctl[0])
+            ctl[1] = atomicAdd(p.nlist, ctl[0]);
+        __syncthreads();
+        if (entry) {
+            // where the path that enters here leaves the tile: the root of the cell
+            const int rc = (int)(ptr16[ly * T + plx] >> 1), cy = rc >> 6, cx = rc & (T - 1);
+            const unsigned rb = pk[(cy + 1) * RP + cx + XO];
+            const int32_t slot = tile * SLOTS + tid;
+            p.list[ctl[1] + at] = slot;
+            p.next[slot] = leaves_tile(rb, cy, cx, th, tw)
+                               ? exit_slot(p, tx, ty, cy, cx, (int)(rb & HT_DIR_CODE))
+                               : TERMINAL;
+        }
+    }
+
 }
 
 // stage C cell words: lo32 = [31:24] signed receiver offset inside the tile (0 =
@@ -1126,15 +998,12 @@ int make_packed_map(CUtensorMap &map, const uint8_t *packed, int64_t packed_ld, 
                            rows + halo_top + halo_bot, cols, packed_ld, RP, RH, false);
 }
 
-template <typename V, int WMODE, bool FINAL>
-int launch_tile(const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
+template <bool FINAL>
+int launch_f64(const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
 {
-    auto kern = acc_tile_kernel<V, WMODE, FINAL>;
-    // counts keep 4 (stage A) or 8 (stage C) bytes per cell, fp64 sums the full layout
-    const int smem = std::is_same<V, double>::value ? SM_TOTAL
-                                                    : SM_VAL + T * T * (FINAL ? 8 : 4) + 16;
-    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<p.tiles_x * p.tiles_y, THREADS, smem, st>>>(map, p);
+    auto kern = acc_f64_kernel<FINAL>;
+    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMD_TOTAL));
+    kern<<<p.tiles_x * p.tiles_y, THREADS, SMD_TOTAL, st>>>(map, p);
     HT_LAUNCH_CHECK();
     return 0;
 }
@@ -1163,7 +1032,7 @@ int dispatch_tile(int mode, const CUtensorMap &map, const AccArgs &p, cudaStream
     switch (mode) {
     case W_ONE: return launch_cnt<W_ONE, FINAL>(map, p, st);
     case W_TAINT: return launch_cnt<W_TAINT, FINAL>(map, p, st);
-    case W_F32: return launch_tile<double, W_F32, FINAL>(map, p, st);
+    case W_F32: return launch_f64<FINAL>(map, p, st);
     }
     return HT_ERR_ARG;
 }
