@@ -34,6 +34,14 @@ def empty_padded(rows: int, cols: int, dtype: torch.dtype, device, align_elems: 
 
 
 def as_2d(a: ArrayLike) -> ArrayLike:
+    """(rows, cols) view of a raster.  Lazy arrays (``dask.array`` as returned by
+    ``hydrotools.raster.from_raster``, /root/reference/src/hydrotools/raster.py:773-791)
+    are materialised here: the kernels want the whole band in HBM, and masked values
+    are recognised by the nodata value / NaN as in the reference (raster.py:788)."""
+    if not isinstance(a, (np.ndarray, torch.Tensor)) and hasattr(a, "compute"):
+        a = a.compute()
+    if isinstance(a, np.ma.MaskedArray):
+        a = np.ma.getdata(a)
     if a.ndim == 3 and a.shape[0] == 1:
         a = a[0]
     if a.ndim != 2:

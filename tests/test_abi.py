@@ -61,3 +61,22 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in src and "oracle/" not in src.replace(
                     "oracle/gdaldem.c", "").replace("oracle/rwatershed.c", "").replace(
                     "oracle/flowacc.c", ""), f
+
+
+def test_lazy_arrays_are_materialised():
+    """dask interop of the array-level API: anything with .compute() (dask.array, as
+    hydrotools.raster.from_raster returns) is accepted; (1, rows, cols) is squeezed."""
+    import numpy as np
+    from hydrotools.cuda import _device as D
+
+    class Lazy:
+        def __init__(self, a):
+            self._a = a
+
+        def compute(self):
+            return self._a
+
+    a = np.ma.masked_equal(np.arange(12, dtype=np.float32).reshape(1, 3, 4), 5)
+    out = D.as_2d(Lazy(a))
+    assert isinstance(out, np.ndarray) and not isinstance(out, np.ma.MaskedArray)
+    assert out.shape == (3, 4) and out[1, 1] == 5
