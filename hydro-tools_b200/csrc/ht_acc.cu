@@ -608,7 +608,9 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     if (inflow) {
         const unsigned i_lo = (unsigned)(inflow & 0xFFFFu), i_hi = (unsigned)(inflow >> 16);
         int cur = ely * T + elx;
-        for (;;) {
+        // a path visits a cell once; the bound only matters for a cyclic (corrupt)
+        // direction raster, which must not hang the GPU
+        for (int step = 0; step < T * T; step++) {
             const unsigned old = atomicAdd(&lo32[cur], i_lo);
             if (i_hi)
                 atomicAdd(&hi32[cur], i_hi);

@@ -176,3 +176,25 @@ def test_path_level_api(hc, golden, tmp_path):
     np.testing.assert_allclose(mean[ok], (e[ok] / cnt[ok]).astype(np.float32), rtol=1e-5)
     ca, _ = _io.read_raster(str(tmp_path / "ca.tif"))
     np.testing.assert_allclose(ca[ok], cnt[ok] * 25.0 / 1e6, rtol=1e-12)
+
+
+def test_cyclic_direction_raster_terminates(hc):
+    """A corrupt direction raster (two cells pointing at each other, fed by a chain)
+    must neither hang nor disturb the cells that are not downstream of the cycle."""
+    dem = oracle.synth_dem(11, 200, 260)
+    fd, _ = oracle.rwatershed(dem, None, 10.0, 10.0)
+    fd = fd.copy()
+    fd[100, 100], fd[100, 101] = 8, 4   # E <-> W
+    fd[100, 99] = 8                     # flows into the cycle
+    got = hc.flow_accumulation_arrays(fd)
+    exp = oracle.flowacc(fd)            # Kahn queue: the cycle is never released
+    # cells whose value does not depend on the cycle: everything the oracle resolved
+    # outside the cycle's downstream (the cycle has none) and outside the cycle itself
+    stuck = np.zeros(fd.shape, bool)
+    stuck[100, 100] = stuck[100, 101] = True
+    np.testing.assert_array_equal(got[~stuck], exp[~stuck])
+    # weighted mode (pointer doubling in both stages) terminates as well
+    w = oracle.synth_weight(11, 200, 260)
+    gw = hc.flow_accumulation_arrays(fd, w)
+    ew = oracle.flowacc(fd, w)
+    np.testing.assert_allclose(gw[~stuck], ew[~stuck], rtol=1e-5)
