@@ -266,6 +266,7 @@ def run_product(args):
 
     # ---- per-kernel timing (CUDA events on the launching stream) for the roofline
     kernels = engine.time_kernels(iters=max(3, min(args.steps, 10)))
+    resolve_rounds = engine.band.resolve_rounds()
     cells = rows * cols
     # D8 4 B read + 1 B written; accumulation 1 B read + 8 B written (+ the
     # final int8 direction codes, 1 B), split over stage A (reads the packed byte) and
@@ -298,6 +299,7 @@ def run_product(args):
     torch.cuda.empty_cache()
     stencil = terrain_roofline(peak) if world == 1 else terrain_bands(peak, rank, world, barrier, dev)
     if rank == 0:
+        stencil["cpu_baseline"] = terrain_cpu_baseline(TERRAIN_N)
         g, dt = oracle_sample_gcells(2500, COLS, total_rows)
         cpu = {"value": g, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first 2500 rows x {COLS} cols of the same DEM, oracle/rwatershed.c "
@@ -312,6 +314,8 @@ def run_product(args):
             "dtype": "int32", "data": "synthetic", "config": workload_config(world),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "path_roofline": path_roofline, "kernels": kernels,
+            "boundary_graph": {"resolve_rounds": resolve_rounds,
+                               "note": "pointer-doubling rounds of stage B until no node is active"},
             "stencil_roofline": stencil,
             "cpu_baseline": cpu,
         }))
@@ -358,6 +362,21 @@ def terrain_roofline(peak):
     return {"kernel": "terrain_kernel (fused slope+aspect+TRI)", "workload": f"{n}x{n} fp32",
             "ms": ms, "gcells_s": n * n / (ms * 1e-3) / 1e9, "achieved": gbs, "peak": peak,
             "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_cell": 16}
+
+
+def terrain_cpu_baseline(n):
+    """gdaldem is single-threaded and the reference runs it three times (slope, aspect,
+    TRI: elevation.py:41-54, 70-78, 118-126); the oracle restatement computes the three
+    in one pass, on a bounded row sample of the same DEM, one core."""
+    import oracle
+    rows = 1024
+    dem = oracle.synth_dem(SEED, rows, n, row0=0, total_rows=n)
+    t0 = time.perf_counter()
+    oracle.gdaldem(dem, None, CSX, CSY)
+    dt = time.perf_counter() - t0
+    return {"value": rows * n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {rows} rows x {n} cols, oracle/gdaldem.c (slope + aspect + TRI in one "
+                      f"pass; the reference spawns gdaldem once per output), {dt:.1f} s"}
 
 
 def terrain_bands(peak, rank, world, barrier, dev):

@@ -302,6 +302,13 @@ class CudaBand:
                     self.ws.data_ptr(), self.ws.numel(), None, self.D.stream_ptr())
         self._launches += 1
 
+    def resolve_rounds(self) -> int:
+        """Pointer-doubling rounds stage B needs on the current boundary graph."""
+        r = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.N.call("ht_acc_resolve", self.rows, self.cols, self._mode, 0, self.ws.data_ptr(),
+                    self.ws.numel(), r.data_ptr(), self.D.stream_ptr())
+        return int(r.item())
+
     def final(self, mode=0, want_dir=True):
         w, wld, has, nd = self._wargs(mode)
         self.N.call("ht_acc_final", self._packed0(), self.pld, self.rows, self.cols, self.row0,

@@ -198,3 +198,27 @@ def test_cyclic_direction_raster_terminates(hc):
     gw = hc.flow_accumulation_arrays(fd, w)
     ew = oracle.flowacc(fd, w)
     np.testing.assert_allclose(gw[~stuck], ew[~stuck], rtol=1e-5)
+
+
+def test_wide_band_shape_mass_balance(hc):
+    """The per-GPU shape of BASELINE.json configs[4] in small: a 100 000-column band
+    (1563 tile columns, 32-bit slot arithmetic near its largest column index); checked
+    on the device through acc(c) = 1 + sum of acc over c's donors."""
+    import torch
+    from hydrotools.cuda import synth
+    rows, cols = 700, 100000
+    buf, ld = synth.synth_dem(5, rows, cols)
+    fd, fa = hc.flow_direction_accumulation_arrays(buf[:, :cols], csx=10.0, csy=10.0)
+    dr = torch.tensor([0, -1, -1, -1, 0, 1, 1, 1, 0], device=fd.device)
+    dc = torch.tensor([0, 1, 0, -1, -1, -1, 0, 1, 1], device=fd.device)
+    f = fd.to(torch.int64)
+    rr = torch.arange(rows, device=fd.device).view(-1, 1).expand(-1, cols)
+    cc = torch.arange(cols, device=fd.device).view(1, -1).expand(rows, -1)
+    edge = (rr == 0) | (cc == 0) | (rr == rows - 1) | (cc == cols - 1)
+    don = (f > 0) & ~edge
+    code = f.clamp(min=0)
+    idx = ((rr + dr[code]) * cols + cc + dc[code])[don]
+    inflow = torch.zeros(rows * cols, dtype=torch.float64, device=fd.device)
+    inflow.index_add_(0, idx, fa[don])
+    assert torch.equal(fa, inflow.view(rows, cols) + 1)
+    assert float(fa[~don].sum()) == rows * cols
