@@ -222,3 +222,54 @@ def test_wide_band_shape_mass_balance(hc):
     inflow.index_add_(0, idx, fa[don])
     assert torch.equal(fa, inflow.view(rows, cols) + 1)
     assert float(fa[~don].sum()) == rows * cols
+
+
+def _plant_slope_ties(dem, csx, csy):
+    """Raise single cells so that the slope towards the SE neighbour over the
+    diagonal EQUALS the slope towards the E neighbour (3-4-5 cells: diagonal 5):
+    (c - SE) / 5 == (c - E) / csx.  Keeps only plantings that leave the DEM
+    conditioned.  Returns (dem, planted cell count)."""
+    a = np.rint(dem.astype(np.float64) * 1000).astype(np.int64)
+    out, n = dem.copy(), 0
+    k_e = int(round(csx))  # run towards E in the 3-4-5 geometry
+    for r in range(40, dem.shape[0] - 40, 13):
+        for c in range(140, dem.shape[1] - 140, 23):
+            ne, e = a[r + 1, c + 1], a[r, c + 1]  # `ne`: the diagonal neighbour (SE here)
+            # want c0 with (c0 - se) * k_e == (c0 - e) * 5  ->  c0 = (5 e - k_e se) / (5 - k_e)
+            num, den = 5 * e - k_e * ne, 5 - k_e
+            if e <= ne or num % den:
+                continue
+            c0 = num // den
+            win = a[r - 1:r + 2, c - 1:c + 2].copy()
+            win[1, 1] = c0
+            if c0 <= e or len(set(win.ravel().tolist())) != 9:
+                continue
+            trial = out.copy()
+            trial[r, c] = np.float32(c0 / 1000.0)
+            if int(round(float(trial[r, c]) * 1000)) != c0:
+                continue
+            if oracle.check_conditioned(trial[r - 3:r + 4, c - 3:c + 4].copy(), None)[1] != 0:
+                continue
+            out, n = trial, n + 1
+            a[r, c] = c0
+    return out, n
+
+
+@pytest.mark.parametrize("csx,csy", [(3.0, 4.0), (4.0, 3.0), (30.0, 10.0), (10.0, 10.0)])
+def test_plain_tiles_anisotropic(hc, csx, csy):
+    """Rasters large enough to have D8 `plain` tiles (the fp32 fast path), square and
+    anisotropic cells."""
+    dem = oracle.synth_dem(31, 420, 900)
+    check_fd_fa(hc, dem, None, csx, csy)
+
+
+@pytest.mark.parametrize("csx,csy", [(3.0, 4.0), (4.0, 3.0)])
+def test_plain_tiles_exact_slope_ties(hc, csx, csy):
+    """With 3-4-5 cells the diagonal / cardinal slope comparison of rule R4 can tie
+    exactly; GRASS then keeps the diagonal (`<`, not `<=`).  The fp32 fast path must
+    hand such cells to the exact integer / double evaluation to stay bit-identical."""
+    dem, planted = _plant_slope_ties(oracle.synth_dem(31, 420, 900), csx, csy)
+    assert planted >= 10
+    if oracle.check_conditioned(dem, None) != (0, 0):
+        pytest.skip("planting broke the conditioning")
+    check_fd_fa(hc, dem, None, csx, csy)
