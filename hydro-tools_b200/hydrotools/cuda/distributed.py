@@ -119,12 +119,35 @@ class BandEngine:
             band.set_halo_rows(top=False, rows=every[self.rank + 1, 0])
 
     # ----------------------------------------------------------------- hot path
-    def flow_direction_accumulation(self, mode: int = 0):
+    def flow_direction_accumulation(self, mode: int = 0, positive_only: bool = True):
+        """D8 + accumulation of this rank's band (results(): direction int8, accumulation
+        fp64).  ``positive_only=False`` reproduces r.watershed without ``-a``
+        (/root/reference/src/hydrotools/watershed.py:52-54): accumulation is negative
+        at edge cells and below cells whose sign r.watershed flipped -- a second
+        sharded accumulation over the taint flags decides that."""
         band = self.band
         if self.world > 1:
             self.exchange_halos(2)
         band.direction()
         self.accumulate(mode)
+        if not positive_only:
+            band.stash_accumulation()
+            self.accumulate(band.N.MODE_TAINT)
+            band.apply_sign()
+            self.launches += band.take_launches()
+
+    def flow_accumulation(self, weight, weight_nodata: Optional[float] = None):
+        """Weighted accumulation (FlowAccumulation.calculate(..., "sum"),
+        /root/reference/src/hydrotools/watershed.py:357-382) over the direction grid the
+        last flow_direction_accumulation() left on the device: ``weight`` = this rank's rows
+        of the weight raster.  Returns this rank's rows of the fp64 sums."""
+        band = self.band
+        band.set_weight(weight, weight_nodata)
+        band.stash_accumulation()
+        self.accumulate(band.N.MODE_WEIGHTED)
+        out = band.acc[:, :self.cols].clone()
+        band.unstash_accumulation()
+        return out
 
     def accumulate(self, mode: int = 0):
         band = self.band
@@ -215,6 +238,7 @@ class CudaBand:
         self._launches = 0
         self._tmp = None
         self._mark = None
+        self._acc2 = None
 
     # ---- pointers
     def _dem0(self):
@@ -405,6 +429,24 @@ class CudaBand:
 
     def results(self):
         return self.dir[:, :self.cols], self.acc[:, :self.cols]
+
+    # a second accumulation (taint counts, weights) lands in self.acc: keep the first
+    def stash_accumulation(self):
+        if self._acc2 is None:
+            self._acc2 = torch.empty_like(self.acc)
+        self.acc, self._acc2 = self._acc2, self.acc
+
+    def unstash_accumulation(self):
+        self.acc, self._acc2 = self._acc2, self.acc
+
+    def apply_sign(self):
+        """After stash_accumulation() + a MODE_TAINT run: self.acc holds the taint counts,
+        the stash the cell counts; negate the counts where r.watershed would."""
+        taint = self.acc
+        self.unstash_accumulation()
+        self.N.call("ht_acc_apply_sign", self.acc.data_ptr(), self.ald, taint.data_ptr(), self.ald,
+                    self._packed0(), self.pld, self.rows, self.cols, self.D.stream_ptr())
+        self._launches += 1
 
     def time_kernels(self, iters=5):
         """Average device time of each stage (CUDA events on the launching stream)."""

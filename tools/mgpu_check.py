@@ -27,6 +27,32 @@ for nulls in (False, True):
         fd_all = torch.cat(gfd).cpu().numpy(); fa_all = torch.cat(gfa).cpu().numpy()
         print(f"world={world} nulls={nulls} dir mismatches {(fd_all != efd).sum()} acc mismatches "
               f"{(~((fa_all == efa) | (np.isnan(fa_all) & np.isnan(efa)))).sum()} max acc {np.nanmax(efa)}")
+    # signed accumulation (r.watershed without -a) and weighted accumulation over bands
+    eng.flow_direction_accumulation(positive_only=False)
+    _, fs = eng.results()
+    gfs = [torch.empty_like(fs.contiguous()) for _ in range(world)]
+    dist.all_gather(gfs, fs.contiguous())
+    w_all = oracle.synth_weight(5, total, cols)
+    wsum = eng.flow_accumulation(torch.from_numpy(w_all[rank * rows:(rank + 1) * rows]).cuda())
+    gw = [torch.empty_like(wsum) for _ in range(world)]
+    dist.all_gather(gw, wsum.contiguous())
+    if rank == 0:
+        _, esigned = oracle.rwatershed(dem, -32767.0 if nulls else None, 10.0, 10.0, positive_only=False)
+        signed = torch.cat(gfs).cpu().numpy()
+        same = (signed == esigned) | (np.isnan(signed) & np.isnan(esigned))
+        # weighted: r.watershed's graph (edge cells do not pass flow on), as in tests/test_bands_gpu.py
+        null = np.isnan(efa)
+        edge = np.zeros(dem.shape, bool); edge[[0, -1], :] = True; edge[:, [0, -1]] = True
+        pad = np.pad(null, 1, constant_values=False)
+        for a in (0, 1, 2):
+            for b in (0, 1, 2):
+                edge |= pad[a:a + dem.shape[0], b:b + dem.shape[1]]
+        d = efd.copy(); d[edge & ~null] = 0
+        ew = oracle.flowacc(d, w_all)
+        got = torch.cat(gw).cpu().numpy()
+        m = ~np.isnan(ew)
+        print(f"  signed accumulation mismatches {(~same).sum()}  weighted max rel err "
+              f"{np.max(np.abs(got[m] - ew[m]) / np.maximum(np.abs(ew[m]), 1e-30)):.2e}")
     # terrain over bands
     s, a, t = eng.terrain()
     gs = [torch.empty_like(s.contiguous()) for _ in range(world)]
