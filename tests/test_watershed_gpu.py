@@ -273,3 +273,38 @@ def test_plain_tiles_exact_slope_ties(hc, csx, csy):
     if oracle.check_conditioned(dem, None) != (0, 0):
         pytest.skip("planting broke the conditioning")
     check_fd_fa(hc, dem, None, csx, csy)
+
+
+def _fbm(seed, rows, cols, hurst=0.8):
+    """Spectral-synthesis fractional Brownian surface (natural-looking terrain with pits
+    and flats everywhere once rounded to millimetres), in metres."""
+    rng = np.random.default_rng(seed)
+    fy = np.fft.fftfreq(rows)[:, None]
+    fx = np.fft.rfftfreq(cols)[None, :]
+    f = np.sqrt(fy * fy + fx * fx)
+    f[0, 0] = 1.0
+    amp = f ** (-(hurst + 1.0))
+    amp[0, 0] = 0.0
+    spec = amp * np.exp(2j * np.pi * rng.random(amp.shape))
+    z = np.fft.irfft2(spec, s=(rows, cols))
+    z = (z - z.min()) / (z.max() - z.min())
+    return (z * 800.0).astype(np.float32)
+
+
+def test_natural_terrain_conditioned_by_rank(hc):
+    """SURVEY.md 8(d)'s harder case: a natural fBm surface (no built-in tilt, valleys
+    in every direction), hydrologically conditioned the way the bundled DEM is in
+    test_conditioned_bundled_dem -- elevation := r.watershed's own A* pop rank -- so
+    that rivers wander for thousands of cells through tiles and bands."""
+    raw = _fbm(7, 1100, 1400)
+    assert oracle.check_conditioned(raw, None)[0] > 0  # the raw surface has pits
+    dem = oracle.condition_by_rank(raw, None, 10.0, 10.0)
+    assert oracle.check_conditioned(dem, None) == (0, 0)
+    fd, fa = check_fd_fa(hc, dem, None, 10.0, 10.0)
+    check_fd_fa(hc, dem, None, 10.0, 10.0, positive_only=False)
+    assert fa.max() > 1e5
+    # and in row bands on one device
+    from test_bands_gpu import run_bands
+    bfd, bfa = run_bands(dem, [0, 300, 640, 1100], None, 10.0, 10.0, delta=True)
+    np.testing.assert_array_equal(bfd, fd)
+    np.testing.assert_array_equal(bfa, fa)
