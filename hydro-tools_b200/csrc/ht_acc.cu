@@ -126,6 +126,11 @@ __host__ __device__ constexpr int link_offset_of(int code)
     return code == 1 ? -T + 1 : code == 2 ? -T : code == 3 ? -T - 1 : code == 4 ? -1
          : code == 5 ? T - 1 : code == 6 ? T : code == 7 ? T + 1 : code == 8 ? 1 : 0;
 }
+__host__ __device__ constexpr int link_offset_pitch(int code, int pitch)
+{
+    return code == 1 ? -pitch + 1 : code == 2 ? -pitch : code == 3 ? -pitch - 1 : code == 4 ? -1
+         : code == 5 ? pitch - 1 : code == 6 ? pitch : code == 7 ? pitch + 1 : code == 8 ? 1 : 0;
+}
 // the same as a packed table of signed bytes: codes 1-4 = -63, -64, -65, -1; 5-8 = 63, 64, 65, 1
 __device__ __forceinline__ int link_offset(unsigned code)
 {
@@ -515,9 +520,14 @@ acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // inflow split 16 / rest, so the low field never carries into the offset
 // (<= 256 walkers x 65535 + 4096 < 2^24), and the atomic that adds the low part
 // returns the link to follow.
+// Rows of the two count arrays are CP = 68 words apart: with a pitch of 64 every cell
+// of the tile's first / last column falls into one bank, and the walkers that start
+// there (one lane per perimeter cell, moving in step along parallel paths) would
+// serialise 32-way on every atomic.
+constexpr int CP = T + 4;
 constexpr int SMF_LO = T * T;               // after the 64x64 packed tile
-constexpr int SMF_HI = SMF_LO + T * T * 4;
-constexpr int SMF_LUT = SMF_HI + T * T * 4; // uint32[16] code -> offset field
+constexpr int SMF_HI = SMF_LO + T * CP * 4;
+constexpr int SMF_LUT = SMF_HI + T * CP * 4; // uint32[16] code -> offset field
 constexpr int SMF_BAR = SMF_LUT + 64;
 constexpr int SMF_TOTAL = SMF_BAR + 16;
 
@@ -543,11 +553,11 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         ht::tma_load_2d(pk, &map, (int)x0, (int)y0 + p.halo_top, &bar);
     }
     if (tid < 16)
-        lut[tid] = ((unsigned)link_offset_of(tid) & 0xFFu) << 24;
+        lut[tid] = ((unsigned)link_offset_pitch(tid, CP) & 0xFFu) << 24;
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
     // thread -> 4 consecutive cells of a row, 4 passes of 16 rows (as in stage A)
     const int q4 = 4 * (tid & 15), r0 = tid >> 4;
-    const int cbase = r0 * T + q4;
+    const int cbase = r0 * CP + q4; // in the count arrays
     const bool wide = q4 + 3 < tw;
 
     // tile-local counts and this tile's resolved inflow while the TMA is in flight
@@ -598,8 +608,8 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                                   !(((rm | cm[j]) >> code) & 1u);
                 wd[j] = (link ? lut[code] : 0u) | cnt[j];
             }
-            *reinterpret_cast<uint4 *>(lo32 + cbase + i * 16 * T) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-            *reinterpret_cast<uint4 *>(hi32 + cbase + i * 16 * T) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(lo32 + cbase + i * 16 * CP) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            *reinterpret_cast<uint4 *>(hi32 + cbase + i * 16 * CP) = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     __syncthreads();
@@ -607,7 +617,7 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     // ---- walkers: one per entry cell with inflow
     if (inflow) {
         const unsigned i_lo = (unsigned)(inflow & 0xFFFFu), i_hi = (unsigned)(inflow >> 16);
-        int cur = ely * T + elx;
+        int cur = ely * CP + elx;
         // a path visits a cell once; the bound only matters for a cyclic (corrupt)
         // direction raster, which must not hang the GPU
         for (int step = 0; step < T * T; step++) {
@@ -630,8 +640,8 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         const int ly = r0 + 16 * i;
         if (ly >= th || q4 >= tw)
             break;
-        const uint4 l4 = *reinterpret_cast<const uint4 *>(lo32 + cbase + i * 16 * T);
-        const uint4 h4 = *reinterpret_cast<const uint4 *>(hi32 + cbase + i * 16 * T);
+        const uint4 l4 = *reinterpret_cast<const uint4 *>(lo32 + cbase + i * 16 * CP);
+        const uint4 h4 = *reinterpret_cast<const uint4 *>(hi32 + cbase + i * 16 * CP);
         const unsigned wq = *reinterpret_cast<const unsigned *>(pk + ly * T + q4);
         const unsigned lo[4] = {l4.x, l4.y, l4.z, l4.w}, hi[4] = {h4.x, h4.y, h4.z, h4.w};
         double a[4];
