@@ -1,0 +1,235 @@
+// ht_filter.cu -- moving-window filter over an arbitrary boolean kernel.
+//
+// Replaces the numba kernel of hydrotools.interpolate.custom_raster_filter /
+// raster_filter (/root/reference/src/hydrotools/interpolate.py:42-64 `apply_filter`
+// under `da.map_overlap(depth, boundary=nan)`, :94-107; reducers :147-222) for the
+// reducers sum, min, max, diff, mean, std, variance: for every non-NaN cell the
+// reducer of the cells the kernel selects in the window
+//     rows i - i_start .. i + i_end,  cols j - j_start .. j + j_end,
+//     i_start = ceil((kh - 1) / 2), i_end = kh - 1 - i_start   (likewise for columns)
+// with NaN outside the raster; sample and reducer in fp64 like the reference
+// (np.nansum / nanmean / nanstd / nanvar on a float64 sample), result fp32, NaN
+// where the centre is NaN or no selected cell holds data.  
+//
+// Kernel: one CTA per 32 x 128 output tile; the tile plus its halo (kernel edge
+// <= 33 => halo <= 16) arrives as ONE TMA box, out-of-raster cells filled with NaN
+// by the TMA unit -- the reference's `boundary=nan` for free.  256 threads, 16
+// cells each (lane -> consecutive columns: conflict-free LDS), the set kernel cells
+// as a table of shared-memory offsets in the kernel parameters (constant bank).
+// 4 B read + 4 B written per cell; HBM-bound for small kernels, bound by the fp64
+// adds / LDS for large ones (work = cells x set kernel cells).
+#include "ht_common.cuh"
+
+namespace {
+
+constexpr int TW = 128, TH = 32, THREADS = 256;
+constexpr int MAXK = 33;  // largest kernel edge
+constexpr int CELLS = TW * TH / THREADS;
+enum { M_SUM = 0, M_MIN, M_MAX, M_DIFF, M_MEAN, M_STD, M_VAR, M_COUNT };
+
+struct FilterArgs {
+    int64_t rows, cols;
+    int halo_top;
+    int tiles_x, tiles_y;
+    int has_nodata;
+    float nodata;
+    int n_off;          // set kernel cells
+    int bw, bh;         // TMA box
+    int hx0a, hy0;      // left halo (rounded up to 4 columns), top halo
+    float *out;
+    int64_t out_ld;
+    int16_t off[MAXK * MAXK]; // shared-memory offsets of the set kernel cells, relative to the centre
+};
+
+template <int METHOD>
+__global__ void __launch_bounds__(THREADS, 2)
+filter_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ FilterArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    float *s = reinterpret_cast<float *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+    const int64_t x0 = (int64_t)tx * TW, y0 = (int64_t)ty * TH;
+    if (tid == 0) {
+        ht::tma_prefetch_desc(&map);
+        ht::mbar_init(&bar, 1);
+        ht::fence_mbar_init();
+        ht::mbar_expect_tx(&bar, (uint32_t)(p.bw * p.bh * 4));
+        ht::tma_load_2d(s, &map, (int)x0 - p.hx0a, (int)y0 - p.hy0 + p.halo_top, &bar);
+    }
+    __syncthreads();
+    ht::mbar_wait(&bar, 0);
+    if (p.has_nodata) { // the reference fills masked cells with NaN before filtering
+        for (int i = tid; i < p.bw * p.bh; i += THREADS)
+            if (s[i] == p.nodata)
+                s[i] = __int_as_float(0x7fc00000);
+        __syncthreads();
+    }
+
+    // thread -> rows 4 * warp + i, columns lane + 32 * j
+    int c[CELLS];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            c[4 * i + j] = (p.hy0 + 4 * warp + i) * p.bw + p.hx0a + lane + 32 * j;
+
+    float res[CELLS];
+    if (METHOD == M_MIN || METHOD == M_MAX || METHOD == M_DIFF) {
+        float mn[CELLS], mx[CELLS];
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            mn[k] = __int_as_float(0x7f800000);
+            mx[k] = __int_as_float(0xff800000);
+        }
+        for (int o = 0; o < p.n_off; o++) {
+            const int d = p.off[o];
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                const float v = s[c[k] + d];
+                mn[k] = fminf(mn[k], v); // fminf / fmaxf ignore NaN
+                mx[k] = fmaxf(mx[k], v);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            const bool any = mx[k] >= mn[k];
+            const float r = METHOD == M_MIN ? mn[k] : METHOD == M_MAX ? mx[k]
+                          : (float)((double)mx[k] - (double)mn[k]);
+            res[k] = any ? r : __int_as_float(0x7fc00000);
+        }
+    }
+    else {
+        double sum[CELLS];
+        int n[CELLS];
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            sum[k] = 0.0;
+            n[k] = 0;
+        }
+        for (int o = 0; o < p.n_off; o++) {
+            const int d = p.off[o];
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                const float v = s[c[k] + d];
+                if (v == v) {
+                    sum[k] += (double)v;
+                    n[k]++;
+                }
+            }
+        }
+        if (METHOD == M_SUM || METHOD == M_MEAN) {
+#pragma unroll
+            for (int k = 0; k < CELLS; k++)
+                res[k] = n[k] ? (float)(METHOD == M_SUM ? sum[k] : sum[k] / (double)n[k])
+                              : __int_as_float(0x7fc00000);
+        }
+        else { // two passes like np.nanstd / np.nanvar: mean, then squared deviations
+            double ss[CELLS];
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                sum[k] = n[k] ? sum[k] / (double)n[k] : 0.0; // mean
+                ss[k] = 0.0;
+            }
+            for (int o = 0; o < p.n_off; o++) {
+                const int d = p.off[o];
+#pragma unroll
+                for (int k = 0; k < CELLS; k++) {
+                    const float v = s[c[k] + d];
+                    if (v == v) {
+                        const double e = (double)v - sum[k];
+                        ss[k] = fma(e, e, ss[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                const double var = n[k] ? ss[k] / (double)n[k] : 0.0;
+                res[k] = n[k] ? (float)(METHOD == M_VAR ? var : sqrt(var)) : __int_as_float(0x7fc00000);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t gr = y0 + 4 * warp + i;
+        if (gr >= p.rows)
+            break;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t gc = x0 + lane + 32 * j;
+            if (gc >= p.cols)
+                continue;
+            const float centre = s[c[4 * i + j]];
+            p.out[gr * p.out_ld + gc] = centre == centre ? res[4 * i + j] : __int_as_float(0x7fc00000);
+        }
+    }
+}
+
+template <int METHOD>
+int launch(const CUtensorMap &map, const FilterArgs &p, cudaStream_t st)
+{
+    auto kern = filter_kernel<METHOD>;
+    const int smem = p.bw * p.bh * 4;
+    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<p.tiles_x * p.tiles_y, THREADS, smem, st>>>(map, p);
+    HT_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace
+
+// kernel_host: kh x kw bytes in HOST memory (non-zero = cell selected), kh, kw <= 33.
+// method: 0 sum, 1 min, 2 max, 3 diff, 4 mean, 5 std, 6 variance.
+// halo_top / halo_bot: valid rows of the neighbour bands directly above / below
+// `src` in the same allocation (0 = that side is the edge of the raster, NaN beyond).
+extern "C" int ht_window_filter_f32(const float *src, int64_t rows, int64_t cols, int64_t ld,
+                                    int has_nodata, float nodata,
+                                    const unsigned char *kernel_host, int kh, int kw, int method,
+                                    float *out, int64_t out_ld, int halo_top, int halo_bot,
+                                    void *stream)
+{
+    if (!src || !out || !kernel_host || rows < 0 || cols < 0 || ld < cols || out_ld < cols ||
+        kh < 1 || kw < 1 || kh > MAXK || kw > MAXK || method < 0 || method >= M_COUNT ||
+        halo_top < 0 || halo_bot < 0)
+        return HT_ERR_ARG;
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    FilterArgs p;
+    const int i_start = kh / 2, i_end = kh - 1 - i_start; // ceil((kh - 1) / 2) == kh / 2
+    const int j_start = kw / 2, j_end = kw - 1 - j_start;
+    p.rows = rows; p.cols = cols;
+    p.halo_top = halo_top;
+    p.tiles_x = ht::cdiv(cols, TW); p.tiles_y = ht::cdiv(rows, TH);
+    p.has_nodata = (has_nodata && nodata == nodata) ? 1 : 0;
+    p.nodata = nodata;
+    p.hy0 = i_start;
+    p.hx0a = (j_start + 3) / 4 * 4;
+    p.bw = TW + p.hx0a + (j_end + 3) / 4 * 4;
+    p.bh = TH + i_start + i_end;
+    p.out = out; p.out_ld = out_ld;
+    p.n_off = 0;
+    for (int ki = 0; ki < kh; ki++)
+        for (int kj = 0; kj < kw; kj++)
+            if (kernel_host[ki * kw + kj])
+                p.off[p.n_off++] = (int16_t)((ki - i_start) * p.bw + (kj - j_start));
+    CUtensorMap map;
+    const float *base = src - (int64_t)halo_top * ld;
+    int rc = ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,
+                             rows + halo_top + halo_bot, cols, ld, p.bw, p.bh, true);
+    if (rc)
+        return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (method) {
+    case M_SUM: return launch<M_SUM>(map, p, st);
+    case M_MIN: return launch<M_MIN>(map, p, st);
+    case M_MAX: return launch<M_MAX>(map, p, st);
+    case M_DIFF: return launch<M_DIFF>(map, p, st);
+    case M_MEAN: return launch<M_MEAN>(map, p, st);
+    case M_STD: return launch<M_STD>(map, p, st);
+    case M_VAR: return launch<M_VAR>(map, p, st);
+    }
+    return HT_ERR_ARG;
+}

@@ -5,6 +5,8 @@ path of bluegeo/hydro-tools:
   (/root/reference/src/hydrotools/watershed.py:30-75, 321-409)
 * ``slope`` / ``aspect`` / ``terrain_ruggedness_index``
   (/root/reference/src/hydrotools/elevation.py:24-56, 59-80, 106-128)
+* ``raster_filter`` (moving-window reducers;
+  /root/reference/src/hydrotools/interpolate.py:110-247)
 
 Python host code over a C-ABI shared library of hand-written CUDA kernels
 (include/hydrotools_b200.h).  No CPU fallback: importing this package without
@@ -12,6 +14,7 @@ the built library, or calling it without a CUDA device, raises.
 """
 from . import _native  # noqa: F401  (raises ImportError if the .so is missing)
 from .elevation import slope, aspect, terrain_ruggedness_index, terrain  # noqa: F401
+from .interpolate import raster_filter, window_filter  # noqa: F401
 from .watershed import (  # noqa: F401
     FlowAccumulation,
     flow_accumulation_arrays,
@@ -30,4 +33,6 @@ __all__ = [
     "FlowAccumulation",
     "flow_accumulation_arrays",
     "validate_conditioned",
+    "raster_filter",
+    "window_filter",
 ]

@@ -12,7 +12,7 @@ georeferencing tags copied from the template, 512x512 DEFLATE tiles.
 """
 import struct
 import zlib
-from typing import Dict, Optional, Tuple
+from typing import Union,  Dict, Optional, Tuple
 
 import numpy as np
 
@@ -203,6 +203,22 @@ def _fallback_write(a: np.ndarray, template: str, dst: str, nodata) -> None:
 # --------------------------------------------------------------------------
 # public boundary
 # --------------------------------------------------------------------------
+def infer_nodata(dtype) -> Union[float, int, bool]:
+    """Nodata value the reference assigns to a data type
+    (/root/reference/src/hydrotools/utils.py:242-265): the type's minimum for floats and
+    signed integers, its maximum for unsigned integers, False for bool."""
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        return float(np.finfo(dt).min)
+    if dt.kind == "i":
+        return int(np.iinfo(dt).min)
+    if dt.kind == "u":
+        return int(np.iinfo(dt).max)
+    if dt.kind == "b":
+        return False
+    raise KeyError(dt.name)
+
+
 def read_raster(src: str) -> Tuple[np.ndarray, dict]:
     """(2-D array with nodata cells holding the nodata value, metadata)."""
     if HAVE_REFERENCE_IO:

@@ -43,6 +43,8 @@ lib.ht_error_string.argtypes = [_int]
 SIGNATURES = {
     "ht_terrain_fused_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _f64, _int,
                              _p, _p, _p, _i64, _int, _int, _p],
+    "ht_window_filter_f32": [_p, _i64, _i64, _i64, _int, _f32, _p, _int, _int, _int, _p, _i64,
+                             _int, _int, _p],
     "ht_d8_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _i64, _i64, _int, _int,
                   _p, _i64, _p],
     "ht_d8_validate_conditioned_f32": [_p, _i64, _i64, _i64, _int, _f32, _i64, _i64, _int,

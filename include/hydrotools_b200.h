@@ -161,6 +161,20 @@ int ht_acc_apply_sign(double *acc, int64_t acc_ld, const double *taint_acc,
                       int64_t taint_ld, const uint8_t *packed, int64_t packed_ld,
                       int64_t rows, int64_t cols, void *stream);
 
+/* ---- interpolate.raster_filter / custom_raster_filter ------------------------
+ * replaces the numba moving-window kernel `apply_filter` under
+ *   da.map_overlap(depth, boundary=nan)
+ *   /root/reference/src/hydrotools/interpolate.py:42-64, 94-107; reducers :147-222
+ * for an arbitrary boolean kernel (kernel_host: kh x kw bytes in HOST memory, nonzero =
+ * selected, kh, kw <= 33).  Window rows i - kh/2 .. i + kh - 1 - kh/2 (likewise columns),
+ * NaN outside the raster; fp64 sample and reducer, fp32 result, NaN where the centre is
+ * NaN (or equals `nodata`) or no selected cell holds data.
+ * method: 0 sum, 1 min, 2 max, 3 diff (max - min), 4 mean, 5 std, 6 variance (ddof 0). */
+int ht_window_filter_f32(const float *src, int64_t rows, int64_t cols, int64_t ld,
+                         int has_nodata, float nodata, const unsigned char *kernel_host,
+                         int kh, int kw, int method, float *out, int64_t out_ld,
+                         int halo_top, int halo_bot, void *stream);
+
 /* ---- synthetic workloads (BASELINE.json configs 2-5) ----------------------
  * integer-exact fractal DEM / weights, see include/ht_synth.h */
 int ht_synth_dem_f32(float *dem, int64_t rows, int64_t cols, int64_t ld,

@@ -1,0 +1,143 @@
+"""Moving-window filter (reference:
+/root/reference/src/hydrotools/interpolate.py:16-247).
+
+PARITY PINNED: tests/golden/filter.npz holds outputs of the reference's own numba
+code (tools/make_filter_goldens.py cuts it out of the reference file and runs it
+unchanged).  CPU tests pin the numpy restatement (oracle/rasterfilter.py) to them;
+GPU tests compare the CUDA kernel with both."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rasterfilter as orf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+METHODS = ["sum", "min", "max", "diff", "mean", "std", "variance"]
+RTOL = 1e-6  # fp64 accumulation on both sides, float32 results
+
+
+@pytest.fixture(scope="module")
+def fgold():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "filter.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _cases(fgold):
+    return sorted({k.split("__")[0] for k in fgold})
+
+
+def _close(got, exp, what):
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp), err_msg=what)
+    m = ~np.isnan(exp)
+    if m.any():
+        np.testing.assert_allclose(got[m], exp[m], rtol=RTOL,
+                                   atol=1e-6 * float(np.abs(exp[m]).max() + 1), err_msg=what)
+
+
+def test_restatement_matches_reference_goldens(fgold):
+    for c in _cases(fgold):
+        a, k = fgold[f"{c}__in"], fgold[f"{c}__kernel"]
+        for m in METHODS:
+            _close(orf.raster_filter(a, k, m), fgold[f"{c}__{m}"], f"{c} {m}")
+
+
+def test_window_geometry():
+    # interpolate.py:82-85
+    assert orf.window_geometry(3, 3) == (1, 1, 1, 1)
+    assert orf.window_geometry(4, 2) == (2, 1, 1, 0)
+    assert orf.window_geometry(1, 5) == (0, 0, 2, 2)
+    with pytest.raises(IndexError):
+        orf.as_kernel((3,))
+    with pytest.raises(IndexError):
+        orf.as_kernel(np.ones(3, bool))
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/src/hydrotools/interpolate.py"),
+                    reason="reference sources only exist in the build container")
+def test_restatement_matches_live_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "make_filter_goldens", os.path.join(ROOT, "tools", "make_filter_goldens.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    apply_filter, reducers = g.reference_functions()
+    rng = np.random.default_rng(5)
+    a = (rng.random((23, 31)) * 50 - 10).astype(np.float32)
+    a[rng.random(a.shape) < 0.2] = np.nan
+    for kernel in [(3, 3), (2, 5), g.disc(2)]:
+        for m in METHODS:
+            exp = g.reference_filter(apply_filter, reducers[m], a, kernel)
+            _close(orf.raster_filter(a, kernel, m), exp, f"{kernel} {m}")
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_gpu_matches_reference_goldens(hc, fgold):
+    for c in _cases(fgold):
+        a, k = fgold[f"{c}__in"], fgold[f"{c}__kernel"]
+        for m in METHODS:
+            _close(hc.window_filter(a, k, m), fgold[f"{c}__{m}"], f"{c} {m}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,kernel", [
+    ((1, 1), (3, 3)), ((5, 300), (3, 3)), ((300, 5), (1, 7)), ((33, 129), (6, 4)),
+    ((257, 513), (3, 3)), ((700, 900), (6, 4)), ((257, 513), "ring"), ((130, 140), "disc9"),
+    ((70, 150), (33, 33)), ((5, 300), (33, 33)), ((300, 5), "disc9"), ((1, 1), (33, 33)),
+])
+def test_gpu_matches_restatement(hc, shape, kernel):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    a = (rng.random(shape) * 1000).astype(np.float32)
+    a[rng.random(shape) < 0.15] = np.nan
+    if kernel == "disc9":
+        y, x = np.mgrid[-9:10, -9:10]
+        kernel = (x * x + y * y) <= 81
+    elif kernel == "ring":
+        kernel = np.ones((5, 5), bool)
+        kernel[1:4, 1:4] = False
+    for m in METHODS:
+        _close(hc.window_filter(a, kernel, m), orf.raster_filter(a, kernel, m), f"{shape} {m}")
+
+
+@pytest.mark.gpu
+def test_gpu_nodata_value_and_device_tensors(hc):
+    import torch
+    rng = np.random.default_rng(1)
+    a = (rng.random((200, 333)) * 10).astype(np.float32)
+    hole = rng.random(a.shape) < 0.1
+    b = a.copy(); b[hole] = -9999.0
+    a[hole] = np.nan
+    exp = orf.raster_filter(a, (5, 5), "mean")
+    _close(hc.window_filter(b, (5, 5), "mean", nodata=-9999.0), exp, "nodata value")
+    out = hc.window_filter(torch.from_numpy(a).cuda(), (5, 5), "mean")
+    assert out.is_cuda
+    _close(out.cpu().numpy(), exp, "device tensor")
+
+
+@pytest.mark.gpu
+def test_gpu_limits_and_errors(hc):
+    a = np.zeros((10, 10), np.float32)
+    with pytest.raises(NotImplementedError):
+        hc.window_filter(a, (3, 3), "median")
+    with pytest.raises(ValueError):
+        hc.window_filter(a, (35, 3), "sum")  # larger than the 33 x 33 the kernel stages
+    with pytest.raises(IndexError):
+        hc.window_filter(a, (3,), "sum")
+
+
+@pytest.mark.gpu
+def test_gpu_path_level(hc, fgold, tmp_path):
+    from hydrotools.cuda import _io
+    from test_terrain_gpu import _write_template
+    a = fgold["dem_5x5__in"]
+    tmpl, src, dst = str(tmp_path / "t.tif"), str(tmp_path / "a.tif"), str(tmp_path / "f.tif")
+    nd = -32767.0
+    filled = np.where(np.isnan(a), nd, a).astype(np.float32)
+    _write_template(tmpl, filled, nd)
+    _io.write_raster(filled, tmpl, src, nodata=nd)
+    hc.raster_filter(src, (5, 5), "std", dst)
+    got, meta = _io.read_raster(dst)
+    got = np.where(got == meta["nodata"], np.nan, got) if meta["nodata"] == meta["nodata"] else got
+    _close(got.astype(np.float32), fgold["dem_5x5__std"], "path level")
