@@ -298,6 +298,7 @@ def run_product(args):
     del engine
     torch.cuda.empty_cache()
     stencil = terrain_roofline(peak) if world == 1 else terrain_bands(peak, rank, world, barrier, dev)
+    wfilter = window_filter_bench(peak) if world == 1 else None
     if rank == 0:
         stencil["cpu_baseline"] = terrain_cpu_baseline(TERRAIN_N)
         g, dt = oracle_sample_gcells(2500, COLS, total_rows)
@@ -316,7 +317,7 @@ def run_product(args):
             "roofline": roofline, "path_roofline": path_roofline, "kernels": kernels,
             "boundary_graph": {"resolve_rounds": resolve_rounds,
                                "note": "pointer-doubling rounds of stage B until no node is active"},
-            "stencil_roofline": stencil,
+            "stencil_roofline": stencil, "window_filter": wfilter,
             "cpu_baseline": cpu,
         }))
     if world > 1:
@@ -362,6 +363,56 @@ def terrain_roofline(peak):
     return {"kernel": "terrain_kernel (fused slope+aspect+TRI)", "workload": f"{n}x{n} fp32",
             "ms": ms, "gcells_s": n * n / (ms * 1e-3) / 1e9, "achieved": gbs, "peak": peak,
             "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_cell": 16}
+
+
+def window_filter_bench(peak):
+    """SURVEY.md 8(f) N3 (interpolate.raster_filter): 3 x 3 max (streaming: 4 B read +
+    4 B written per cell) and a disc of radius 10 cells, mean (317 samples per cell, fp64
+    like the reference) on 16384^2; CPU baseline: the numpy restatement of the reference's
+    numba loop on a bounded sample, one core."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from hydrotools.cuda import _native as N, _device as D, synth
+    from oracle import rasterfilter as orf
+    n = 16384
+    dem, ld = synth.synth_dem(SEED, n, n)
+    out = torch.empty((n, ld), dtype=torch.float32, device="cuda")
+    st = D.stream_ptr()
+    y, x = np.mgrid[-10:11, -10:11]
+    res = []
+    for name, k, method in (("3x3 max", np.ones((3, 3), np.uint8), "max"),
+                            ("disc r=10 mean", ((x * x + y * y) <= 100).astype(np.uint8), "mean")):
+        k = np.ascontiguousarray(k)
+        code = {"max": 2, "mean": 4}[method]
+
+        def run():
+            N.call("ht_window_filter_f32", dem.data_ptr(), n, n, ld, 0, 0.0,
+                   k.ctypes.data_as(C.c_void_p), k.shape[0], k.shape[1], code, out.data_ptr(), ld,
+                   0, 0, st)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        sample = dem[:256, :2048].cpu().numpy()
+        t0 = time.perf_counter()
+        orf.raster_filter(sample, k.astype(bool), method)
+        dt = time.perf_counter() - t0
+        gbs = n * n * 8 / (ms * 1e-3) / 1e9
+        res.append({"kernel": name, "samples_per_cell": int(k.sum()), "ms": ms,
+                    "gcells_s": n * n / (ms * 1e-3) / 1e9, "achieved": gbs, "peak": peak,
+                    "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_cell": 8,
+                    "cpu_baseline": {"value": sample.size / dt / 1e9, "unit": UNIT, "cores": 1,
+                                     "kind": "port", "sample": f"256 x 2048 cells, oracle/rasterfilter.py, {dt:.2f} s"}})
+    del dem, out
+    torch.cuda.empty_cache()
+    return {"workload": f"{n}x{n} fp32 (next row N3: interpolate.raster_filter)", "cases": res}
 
 
 def terrain_cpu_baseline(n):
