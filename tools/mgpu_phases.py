@@ -30,14 +30,11 @@ for it in range(10):
     band.local(0); mark("stage A")
     band.mark_edges(0); mark("mark band edges")
     band.resolve(True); mark("stage B (roots)")
-    delivered, link = band.band_tables(0); mark("band tables")
+    both = band.band_tables4(); mark("band tables (1 kernel)")
     P = world
-    both = torch.cat([delivered, link.to(torch.int64)])
     every = torch.empty((P * 4, cols), dtype=torch.int64, device=both.device)
-    dist.all_gather_into_tensor(every, both)
-    every = every.view(P, 4, cols)
-    all_d, all_l = every[:, :2], every[:, 2:]; mark("all_gather")
-    base, nxt = HD.build_band_graph(all_d.reshape(P, 2, cols), all_l.reshape(P, 2, cols)); mark("build band graph")
+    dist.all_gather_into_tensor(every, both); mark("all_gather")
+    base, nxt = band.band_graph(every, P); mark("band graph (1 kernel)")
     inflow = band.forest_resolve(base, nxt, 0).view(P, 2, cols); mark("band forest resolve")
     band.resolve_delta(inflow[rank, 0], inflow[rank, 1], 0); mark("stage B delta")
     band.final(0); mark("stage C")
