@@ -131,13 +131,6 @@ __host__ __device__ constexpr int link_offset_pitch(int code, int pitch)
     return code == 1 ? -pitch + 1 : code == 2 ? -pitch : code == 3 ? -pitch - 1 : code == 4 ? -1
          : code == 5 ? pitch - 1 : code == 6 ? pitch : code == 7 ? pitch + 1 : code == 8 ? 1 : 0;
 }
-// the same as a packed table of signed bytes: codes 1-4 = -63, -64, -65, -1; 5-8 = 63, 64, 65, 1
-__device__ __forceinline__ int link_offset(unsigned code)
-{
-    const unsigned tab = code <= 4u ? 0xFFBFC0C1u : 0x0141403Fu;
-    return (int)(signed char)(tab >> (8u * ((code - 1u) & 3u)));
-}
-
 // codes that leave the tile through its west / east / north / south side (bit = code)
 constexpr unsigned EX_W = (1u << 3) | (1u << 4) | (1u << 5), EX_E = (1u << 1) | (1u << 7) | (1u << 8);
 constexpr unsigned EX_N = (1u << 1) | (1u << 2) | (1u << 3), EX_S = (1u << 5) | (1u << 6) | (1u << 7);

@@ -63,8 +63,7 @@ struct D8Args {
 };
 
 // r.watershed's neighbour order ct = 0..7: S,N,W,E,NE,SW,SE,NW (cardinals first)
-// window cell (3x3 row-major) of neighbour ct = {7, 1, 3, 5, 2, 6, 8, 0}
-__device__ __forceinline__ int ct2win(int ct) { return (0x08625317u >> (4 * ct)) & 0xF; }
+// (window cell, 3x3 row-major, of neighbour ct = {7, 1, 3, 5, 2, 6, 8, 0})
 // GRASS direction code of neighbour ct = {6, 2, 4, 8, 1, 5, 7, 3}
 __device__ __forceinline__ int ct2code(int ct) { return (0x37518426u >> (4 * ct)) & 0xF; }
 // GRASS direction code that points at window cell k = {3, 2, 1, 4, 0, 8, 5, 6, 7}

@@ -18,6 +18,9 @@
 // as a table of shared-memory offsets in the kernel parameters (constant bank).
 // 4 B read + 4 B written per cell; HBM-bound for small kernels, bound by the fp64
 // adds / LDS for large ones (work = cells x set kernel cells).
+#include <algorithm>
+#include <new>
+
 #include "ht_common.cuh"
 
 namespace {
@@ -168,6 +171,136 @@ filter_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ F
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Large kernels, sum / mean: row prefix sums + one difference per kernel-row run.
+// The reference's callers filter with discs built from a distance
+// (kernel_from_distance, /root/reference/src/hydrotools/utils.py:408-426;
+// morphology.py:282-289 "mean", :1373-1374 "sum"), i.e. with hundreds to tens of
+// thousands of samples per cell.  With P[y][x] = sum of the valid values of row y left
+// of column x (fp64) and C[y][x] = their number, a run [a, b] of selected cells in
+// kernel row ky contributes P[y][x + b + 1] - P[y][x + a] -- two loads instead of
+// b - a + 1, and no limit on the kernel size.  Columns are clamped to the raster, which
+// is the reference's NaN boundary (nothing to add outside).
+// ---------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 4;
+
+// one CTA per row: exclusive prefix of the valid values / their count, cols + 1 entries
+__global__ void __launch_bounds__(SCAN_THREADS)
+row_prefix_kernel(const float *src, int64_t ld, int64_t rows_all, int64_t cols, int has_nodata,
+                  float nodata, double *P, unsigned *Cn, int64_t pld)
+{
+    __shared__ double wsum[SCAN_THREADS / 32];
+    __shared__ unsigned wcnt[SCAN_THREADS / 32];
+    __shared__ double carry_s;
+    __shared__ unsigned carry_c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t y = blockIdx.x; y < rows_all; y += gridDim.x) {
+        const float *row = src + y * ld;
+        double *Pr = P + y * pld;
+        unsigned *Cr = Cn + y * pld;
+        if (tid == 0) {
+            carry_s = 0.0;
+            carry_c = 0u;
+            Pr[0] = 0.0;
+            Cr[0] = 0u;
+        }
+        __syncthreads();
+        for (int64_t x0 = 0; x0 < cols; x0 += SCAN_THREADS * SCAN_ITEMS) {
+            double v[SCAN_ITEMS];
+            unsigned c[SCAN_ITEMS];
+            double ts = 0.0;
+            unsigned tc = 0u;
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; k++) {
+                const int64_t x = x0 + (int64_t)tid * SCAN_ITEMS + k;
+                float f = x < cols ? row[x] : __int_as_float(0x7fc00000);
+                const bool ok = f == f && !(has_nodata && f == nodata);
+                ts += ok ? (double)f : 0.0;
+                tc += ok ? 1u : 0u;
+                v[k] = ts; // inclusive within the thread
+                c[k] = tc;
+            }
+            // exclusive scan of the per-thread totals across the CTA
+            double ws = ts;
+            unsigned wc = tc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double s2 = __shfl_up_sync(0xffffffffu, ws, o);
+                const unsigned c2 = __shfl_up_sync(0xffffffffu, wc, o);
+                if (lane >= o) {
+                    ws += s2;
+                    wc += c2;
+                }
+            }
+            if (lane == 31) {
+                wsum[warp] = ws;
+                wcnt[warp] = wc;
+            }
+            __syncthreads();
+            double base = carry_s;
+            unsigned cbase = carry_c;
+            for (int w = 0; w < warp; w++) {
+                base += wsum[w];
+                cbase += wcnt[w];
+            }
+            base += ws - ts; // exclusive prefix of this thread
+            cbase += wc - tc;
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; k++) {
+                const int64_t x = x0 + (int64_t)tid * SCAN_ITEMS + k;
+                if (x < cols) {
+                    Pr[x + 1] = base + v[k];
+                    Cr[x + 1] = cbase + c[k];
+                }
+            }
+            __syncthreads();
+            if (tid == SCAN_THREADS - 1) {
+                carry_s = base + ts;
+                carry_c = cbase + tc;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct Run { int16_t ky, a, b; }; // kernel row, first / last selected column (kernel coordinates)
+
+// thread -> one output cell; lanes along x.  P / Cn cover rows -halo_top .. rows + halo_bot.
+__global__ void __launch_bounds__(256)
+run_filter_kernel(const float *src, int64_t ld, int64_t rows, int64_t cols, int halo_top,
+                  int halo_bot, int has_nodata, float nodata, const double *P, const unsigned *Cn,
+                  int64_t pld, const Run *runs, int n_runs, int i_start, int j_start, int mean,
+                  float *out, int64_t out_ld)
+{
+    extern __shared__ Run srun[];
+    for (int i = threadIdx.x; i < n_runs; i += blockDim.x)
+        srun[i] = runs[i];
+    __syncthreads();
+    const int64_t x = (int64_t)blockIdx.x * 128 + (threadIdx.x & 127);
+    const int64_t y0 = ((int64_t)blockIdx.y * 2 + (threadIdx.x >> 7)) * 16;
+    if (x >= cols)
+        return;
+    for (int64_t y = y0; y < min(y0 + 16, rows); y++) {
+        const float centre = src[y * ld + x];
+        double sum = 0.0;
+        unsigned n = 0u;
+        for (int r = 0; r < n_runs; r++) {
+            const Run q = srun[r];
+            const int64_t yy = y + q.ky - i_start;
+            if (yy < -(int64_t)halo_top || yy >= rows + halo_bot)
+                continue;
+            const int64_t xa = min(max(x + q.a - j_start, (int64_t)0), cols);
+            const int64_t xb = min(max(x + q.b - j_start + 1, (int64_t)0), cols);
+            const int64_t at = (yy + halo_top) * pld;
+            sum += P[at + xb] - P[at + xa];
+            n += Cn[at + xb] - Cn[at + xa];
+        }
+        const bool ok = centre == centre && !(has_nodata && centre == nodata) && n;
+        out[y * out_ld + x] = ok ? (float)(mean ? sum / (double)n : sum) : __int_as_float(0x7fc00000);
+    }
+}
+
 template <int METHOD>
 int launch(const CUtensorMap &map, const FilterArgs &p, cudaStream_t st)
 {
@@ -232,4 +365,85 @@ extern "C" int ht_window_filter_f32(const float *src, int64_t rows, int64_t cols
     case M_VAR: return launch<M_VAR>(map, p, st);
     }
     return HT_ERR_ARG;
+}
+
+// Scratch ht_window_filter_runs_f32 needs: row prefix sums (fp64) and counts (u32) of the
+// rows it is given, cols + 1 entries per row (pitch rounded up to 2), plus the run table.
+extern "C" size_t ht_window_filter_runs_workspace_bytes(int64_t rows_with_halos, int64_t cols,
+                                                        int kh)
+{
+    if (rows_with_halos <= 0 || cols <= 0 || kh <= 0)
+        return 256;
+    const int64_t pld = (cols + 2) / 2 * 2;
+    return (size_t)rows_with_halos * pld * 12 + (size_t)kh * 64 * sizeof(Run) + 1024;
+}
+
+// sum (method 0) / mean (method 4) over a boolean kernel of ANY size by row prefix sums.
+// At most 64 runs per kernel row (a disc has one).  ws: device scratch, see above.
+extern "C" int ht_window_filter_runs_f32(const float *src, int64_t rows, int64_t cols, int64_t ld,
+                                         int has_nodata, float nodata,
+                                         const unsigned char *kernel_host, int kh, int kw,
+                                         int method, float *out, int64_t out_ld, int halo_top,
+                                         int halo_bot, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!src || !out || !kernel_host || !ws || rows < 0 || cols < 0 || ld < cols || out_ld < cols ||
+        kh < 1 || kw < 1 || kh > 32767 || kw > 32767 || (method != M_SUM && method != M_MEAN) ||
+        halo_top < 0 || halo_bot < 0)
+        return HT_ERR_ARG;
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    const int64_t rows_all = rows + halo_top + halo_bot;
+    if (ws_bytes < ht_window_filter_runs_workspace_bytes(rows_all, cols, kh))
+        return HT_ERR_WORKSPACE;
+    // runs of selected cells per kernel row
+    Run *hruns = new (std::nothrow) Run[(size_t)kh * 64];
+    if (!hruns)
+        return HT_ERR_ARG;
+    int n_runs = 0;
+    for (int ki = 0; ki < kh; ki++) {
+        int in_row = 0;
+        for (int kj = 0; kj < kw;) {
+            if (!kernel_host[(size_t)ki * kw + kj]) {
+                kj++;
+                continue;
+            }
+            int e = kj;
+            while (e + 1 < kw && kernel_host[(size_t)ki * kw + e + 1])
+                e++;
+            if (++in_row > 64) {
+                delete[] hruns;
+                return HT_ERR_ARG;
+            }
+            hruns[n_runs].ky = (int16_t)ki; hruns[n_runs].a = (int16_t)kj; hruns[n_runs].b = (int16_t)e;
+            n_runs++;
+            kj = e + 1;
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t pld = (cols + 2) / 2 * 2;
+    uint8_t *b = (uint8_t *)(((uintptr_t)ws + 255) / 256 * 256);
+    double *P = (double *)b;
+    unsigned *Cn = (unsigned *)(b + (size_t)rows_all * pld * 8);
+    Run *druns = (Run *)(b + (size_t)rows_all * pld * 12);
+    cudaError_t e = cudaMemcpyAsync(druns, hruns, (size_t)n_runs * sizeof(Run), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st); // hruns is about to go away
+    delete[] hruns;
+    if (e != cudaSuccess)
+        return (int)e;
+    const float *base = src - (int64_t)halo_top * ld;
+    row_prefix_kernel<<<(unsigned)std::min<int64_t>(rows_all, 148 * 8), SCAN_THREADS, 0, st>>>(
+        base, ld, rows_all, cols, has_nodata && nodata == nodata, nodata, P, Cn, pld);
+    HT_LAUNCH_CHECK();
+    const int i_start = kh / 2, j_start = kw / 2;
+    const size_t smem = (size_t)n_runs * sizeof(Run);
+    if (smem > 48 * 1024)
+        HT_CUDA_TRY(cudaFuncSetAttribute(run_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ht::cdiv(cols, 128), (unsigned)ht::cdiv(rows, 32));
+    run_filter_kernel<<<grid, 256, smem, st>>>(src, ld, rows, cols, halo_top, halo_bot,
+                                              has_nodata && nodata == nodata, nodata, P, Cn, pld,
+                                              druns, n_runs, i_start, j_start, method == M_MEAN, out,
+                                              out_ld);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
 }

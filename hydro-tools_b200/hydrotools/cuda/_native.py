@@ -45,6 +45,8 @@ SIGNATURES = {
                              _p, _p, _p, _i64, _int, _int, _p],
     "ht_window_filter_f32": [_p, _i64, _i64, _i64, _int, _f32, _p, _int, _int, _int, _p, _i64,
                              _int, _int, _p],
+    "ht_window_filter_runs_f32": [_p, _i64, _i64, _i64, _int, _f32, _p, _int, _int, _int, _p,
+                                  _i64, _int, _int, _p, C.c_size_t, _p],
     "ht_d8_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _i64, _i64, _int, _int,
                   _p, _i64, _p],
     "ht_d8_validate_conditioned_f32": [_p, _i64, _i64, _i64, _int, _f32, _i64, _i64, _int,
@@ -79,6 +81,8 @@ def _declare():
 _declare()
 lib.ht_acc_workspace_bytes.argtypes = [_i64, _i64]
 lib.ht_acc_workspace_bytes.restype = C.c_size_t
+lib.ht_window_filter_runs_workspace_bytes.argtypes = [_i64, _i64, _int]
+lib.ht_window_filter_runs_workspace_bytes.restype = C.c_size_t
 
 MODE_COUNT, MODE_TAINT, MODE_WEIGHTED = 0, 1, 2
 

@@ -23,7 +23,8 @@ from . import _io
 
 METHODS = {"sum": 0, "min": 1, "max": 2, "diff": 3, "mean": 4, "std": 5, "variance": 6}
 _UNSUPPORTED = ("mode", "median", "percentile", "quantile")
-MAX_KERNEL = 33  # largest kernel edge the CUDA kernel stages (halo of 16 cells)
+MAX_KERNEL = 33  # largest kernel edge the direct kernel stages (halo of 16 cells)
+RUNS_FROM = 64   # sum / mean with at least this many selected cells go through row prefix sums
 
 
 def _as_kernel(kernel: Union[np.ndarray, tuple]) -> np.ndarray:
@@ -38,6 +39,12 @@ def _as_kernel(kernel: Union[np.ndarray, tuple]) -> np.ndarray:
     return np.array(kernel, dtype=bool)
 
 
+def _max_runs(k: np.ndarray) -> int:
+    """Largest number of runs of selected cells in one kernel row."""
+    p = np.pad(k.astype(np.int8), ((0, 0), (1, 0)))
+    return int((np.diff(p, axis=1) == 1).sum(axis=1).max()) if k.size else 0
+
+
 def window_filter(a: D.ArrayLike, kernel: Union[np.ndarray, tuple], method: str,
                   nodata: Optional[float] = None, halo_top: int = 0, halo_bot: int = 0):
     """Array-level ``raster_filter``: float32 (rows, cols) in, float32 out, NaN = no data
@@ -50,9 +57,13 @@ def window_filter(a: D.ArrayLike, kernel: Union[np.ndarray, tuple], method: str,
     if method not in METHODS:
         raise ValueError(f"unknown method {method!r}")
     k = _as_kernel(kernel)
-    if k.shape[0] > MAX_KERNEL or k.shape[1] > MAX_KERNEL:
-        raise ValueError(f"kernels larger than {MAX_KERNEL} x {MAX_KERNEL} are not supported "
-                         f"(got {k.shape[0]} x {k.shape[1]})")
+    big = k.shape[0] > MAX_KERNEL or k.shape[1] > MAX_KERNEL
+    # sum / mean over many cells (the discs of kernel_from_distance the reference filters
+    # with): row prefix sums, any kernel size
+    use_runs = method in ("sum", "mean") and (big or int(k.sum()) >= RUNS_FROM) and _max_runs(k) <= 64
+    if big and not use_runs:
+        raise ValueError(f"{method!r} over kernels larger than {MAX_KERNEL} x {MAX_KERNEL} is not "
+                         f"supported (got {k.shape[0]} x {k.shape[1]}); sum and mean are")
     dev = D.require_cuda()
     on_host = not isinstance(a, torch.Tensor)
     a = D.as_2d(a)
@@ -64,6 +75,15 @@ def window_filter(a: D.ArrayLike, kernel: Union[np.ndarray, tuple], method: str,
     out, out_ld = D.empty_padded(rows, cols, torch.float32, dev, 4)
     kb = np.ascontiguousarray(k, dtype=np.uint8)
     has, nd = D.nodata_args(nodata)
+    if use_runs:
+        need = int(N.lib.ht_window_filter_runs_workspace_bytes(int(a.shape[0]), cols, int(k.shape[0])))
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        N.call("ht_window_filter_runs_f32", buf.data_ptr() + halo_top * ld * 4, rows, cols, ld, has,
+               nd, kb.ctypes.data_as(C.c_void_p), int(k.shape[0]), int(k.shape[1]), METHODS[method],
+               out.data_ptr(), out_ld, halo_top, halo_bot, ws.data_ptr(), ws.numel(),
+               D.stream_ptr())
+        view = out[:, :cols]
+        return D.download(view) if on_host else view
     N.call("ht_window_filter_f32", buf.data_ptr() + halo_top * ld * 4, rows, cols, ld, has, nd,
            kb.ctypes.data_as(C.c_void_p), int(k.shape[0]), int(k.shape[1]), METHODS[method],
            out.data_ptr(), out_ld, halo_top, halo_bot, D.stream_ptr())

@@ -175,6 +175,19 @@ int ht_window_filter_f32(const float *src, int64_t rows, int64_t cols, int64_t l
                          int kh, int kw, int method, float *out, int64_t out_ld,
                          int halo_top, int halo_bot, void *stream);
 
+/* the same filter for sum (0) / mean (4) over a boolean kernel of ANY size (the discs
+ * of kernel_from_distance, /root/reference/src/hydrotools/utils.py:408-426, as used at
+ * morphology.py:282-289 and :1373-1374): row prefix sums in fp64 + one difference per
+ * run of selected cells in a kernel row (<= 64 runs per row).  ws: device scratch of
+ * ht_window_filter_runs_workspace_bytes(rows + halo_top + halo_bot, cols, kh) bytes.
+ * Synchronises the stream once (upload of the run table). */
+size_t ht_window_filter_runs_workspace_bytes(int64_t rows_with_halos, int64_t cols, int kh);
+int ht_window_filter_runs_f32(const float *src, int64_t rows, int64_t cols, int64_t ld,
+                              int has_nodata, float nodata, const unsigned char *kernel_host,
+                              int kh, int kw, int method, float *out, int64_t out_ld,
+                              int halo_top, int halo_bot, void *ws, size_t ws_bytes,
+                              void *stream);
+
 /* ---- synthetic workloads (BASELINE.json configs 2-5) ----------------------
  * integer-exact fractal DEM / weights, see include/ht_synth.h */
 int ht_synth_dem_f32(float *dem, int64_t rows, int64_t cols, int64_t ld,

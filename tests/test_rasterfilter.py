@@ -102,6 +102,24 @@ def test_gpu_matches_restatement(hc, shape, kernel):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,radius", [((300, 400), 20), ((150, 1100), 40), ((64, 64), 50), ((1, 1), 17)])
+def test_gpu_large_discs_by_row_prefix_sums(hc, shape, radius):
+    """sum / mean over distance discs of any size (kernel_from_distance,
+    /root/reference/src/hydrotools/utils.py:408-426): the row-prefix-sum kernel."""
+    rng = np.random.default_rng(radius)
+    a = (rng.random(shape) * 1000).astype(np.float32)
+    a[rng.random(shape) < 0.2] = np.nan
+    y, x = np.mgrid[-radius:radius + 1, -radius:radius + 1]
+    disc = (x * x + y * y) <= radius * radius
+    disc[radius, radius] = False  # kernel_from_distance clears nothing, but a hole makes two runs
+    for m in ("sum", "mean"):
+        _close(hc.window_filter(a, disc, m), orf.raster_filter(a, disc, m), f"{shape} r={radius} {m}")
+    # even-sized rectangle, and the same answer as the direct kernel where both apply
+    rect = np.ones((12, 20), bool)
+    _close(hc.window_filter(a, rect, "mean"), orf.raster_filter(a, rect, "mean"), "rect")
+
+
+@pytest.mark.gpu
 def test_gpu_nodata_value_and_device_tensors(hc):
     import torch
     rng = np.random.default_rng(1)
@@ -122,7 +140,7 @@ def test_gpu_limits_and_errors(hc):
     with pytest.raises(NotImplementedError):
         hc.window_filter(a, (3, 3), "median")
     with pytest.raises(ValueError):
-        hc.window_filter(a, (35, 3), "sum")  # larger than the 33 x 33 the kernel stages
+        hc.window_filter(a, (35, 3), "max")  # larger than the 33 x 33 the direct kernel stages
     with pytest.raises(IndexError):
         hc.window_filter(a, (3,), "sum")
 

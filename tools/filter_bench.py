@@ -36,3 +36,21 @@ for name, k, method in [("3x3 mean", np.ones((3, 3), np.uint8), 4), ("3x3 max", 
     ms = e0.elapsed_time(e1) / 5
     print(f"{name:16s} {int(k.sum()):5d} cells  {ms:8.3f} ms  {n * n / ms / 1e6:8.1f} Gcells/s  "
           f"{n * n * 8 / ms / 1e6:7.0f} GB/s (8 B/cell)  {n * n * int(k.sum()) / ms / 1e9:7.1f} Gsamples/ms")
+
+
+# large discs through the public API (row prefix sums): sum / mean, any radius
+import hydrotools.cuda as hc
+view = dem[:, :n]
+for r in (10, 50, 100):
+    k = disc(r).astype(bool)
+    for _ in range(2):
+        hc.window_filter(view, k, "mean")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        hc.window_filter(view, k, "mean")
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"disc r={r:<3d} mean (prefix sums) {int(k.sum()):6d} cells  {ms:8.3f} ms  {n * n / ms / 1e6:8.1f} Gcells/s  "
+          f"{n * n * int(k.sum()) / ms / 1e9:8.1f} Gsamples/ms equivalent")
