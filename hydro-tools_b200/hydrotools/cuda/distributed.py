@@ -202,6 +202,35 @@ class BandEngine:
         self.launches += self.band.take_launches()
         return out
 
+    def window_filter(self, kernel, method: str):
+        """Moving-window reducer (hydrotools.cuda.window_filter,
+        /root/reference/src/hydrotools/interpolate.py:110-247) of this rank's rows of the
+        DEM; the rows of the neighbour bands the window reaches into travel in one
+        all-gather, like the stencil halos."""
+        from .interpolate import _as_kernel, window_filter
+        band, P = self.band, self.world
+        k = _as_kernel(kernel)
+        i0 = k.shape[0] // 2
+        i1 = k.shape[0] - 1 - i0
+        own = band.dem_view()
+        top = bot = None
+        d = max(i0, i1)
+        if P > 1 and d > 0:
+            if d > self.rows:
+                raise ValueError("the kernel reaches beyond the neighbouring band")
+            send = torch.stack([band.edge_rows(top=True, depth=d), band.edge_rows(top=False, depth=d)])
+            every = torch.empty((P,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+            dist.all_gather_into_tensor(every.view(P * 2, d, self.cols), send, group=self.group)
+            if self.rank > 0 and i0:
+                top = every[self.rank - 1, 1][d - i0:]      # last i0 rows of the band above
+            if self.rank < P - 1 and i1:
+                bot = every[self.rank + 1, 0][:i1]          # first i1 rows of the band below
+        parts = [x for x in (top, own, bot) if x is not None]
+        a = torch.cat(parts) if len(parts) > 1 else own
+        return window_filter(a, k, method, nodata=getattr(band, "nodata", None),
+                             halo_top=0 if top is None else int(top.shape[0]),
+                             halo_bot=0 if bot is None else int(bot.shape[0]))
+
     def results(self):
         return self.band.results()
 

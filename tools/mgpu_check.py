@@ -53,6 +53,24 @@ for nulls in (False, True):
         m = ~np.isnan(ew)
         print(f"  signed accumulation mismatches {(~same).sum()}  weighted max rel err "
               f"{np.max(np.abs(got[m] - ew[m]) / np.maximum(np.abs(ew[m]), 1e-30)):.2e}")
+    # moving-window filter over bands (direct kernel and row prefix sums)
+    from oracle import rasterfilter as orf
+    for kern, meth in (((5, 7), "std"), ((4, 4), "max"), ("disc", "mean")):
+        if kern == "disc":
+            yy, xx = np.mgrid[-12:13, -12:13]
+            kern = (xx * xx + yy * yy) <= 144
+        fr = eng.window_filter(kern, meth)
+        gfr = [torch.empty_like(fr.contiguous()) for _ in range(world)]
+        dist.all_gather(gfr, fr.contiguous())
+        if rank == 0:
+            a = dem.astype(np.float32).copy()
+            if nulls:
+                a[a == -32767.0] = np.nan
+            e = orf.raster_filter(a, kern, meth)
+            g = torch.cat(gfr).cpu().numpy()
+            m = ~np.isnan(e)
+            print(f"  filter {meth}: mask equal {np.array_equal(np.isnan(g), np.isnan(e))}, max rel err "
+                  f"{np.max(np.abs(g[m] - e[m]) / np.maximum(np.abs(e[m]), 1e-3)):.1e}")
     # terrain over bands
     s, a, t = eng.terrain()
     gs = [torch.empty_like(s.contiguous()) for _ in range(world)]
