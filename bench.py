@@ -89,7 +89,7 @@ class ClockSampler:
             time.sleep(0.002)
 
     def __enter__(self):
-        if self.nv:
+        if self.nv and not os.environ.get("HT_BENCH_NO_CLOCKS"):
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
         return self
@@ -195,6 +195,11 @@ def run_product(args):
     def step():
         engine.flow_direction_accumulation()
 
+    if world > 1:
+        # NCCL sets up its channels lazily on the first collectives of each size; keep that
+        # out of the W warm-up steps the caller asked for
+        for _ in range(5):
+            step()
     for _ in range(args.warmup):
         step()
     launches0 = engine.launches

@@ -42,9 +42,15 @@ for it in range(10):
     for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
         tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
 dist.barrier()
+names = list(tot.keys())
+mine = torch.tensor([tot[k] / 10 for k in names], dtype=torch.float64, device="cuda")
+allr = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(allr, mine)
 if rank == 0:
-    s = 0
-    for k, v in tot.items():
-        print(f"{k:24s} {v / 10:8.4f} ms"); s += v / 10
-    print(f"{'sum':24s} {s:8.4f} ms")
+    sums = [float(t.sum()) for t in allr]
+    slow = max(range(world), key=lambda r: sums[r])
+    print("per-rank sums (ms):", " ".join(f"{x:.3f}" for x in sums))
+    print(f"{'phase':24s} {'rank 0':>9s} {'rank ' + str(slow) + ' (slowest)':>18s}")
+    for i, k in enumerate(names):
+        print(f"{k:24s} {float(allr[0][i]):9.4f} {float(allr[slow][i]):18.4f}")
 dist.destroy_process_group()
