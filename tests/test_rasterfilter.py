@@ -159,3 +159,20 @@ def test_gpu_path_level(hc, fgold, tmp_path):
     got, meta = _io.read_raster(dst)
     got = np.where(got == meta["nodata"], np.nan, got) if meta["nodata"] == meta["nodata"] else got
     _close(got.astype(np.float32), fgold["dem_5x5__std"], "path level")
+
+
+# ------------------------------------------------------------------ host logic (CPU)
+def test_host_kernel_helpers(hc):
+    from hydrotools.cuda import interpolate as I
+    assert I._as_kernel((2, 3)).shape == (2, 3) and I._as_kernel((2, 3)).all()
+    with pytest.raises(IndexError):
+        I._as_kernel((1, 2, 3))
+    k = np.array([[1, 0, 1, 1, 0, 1], [0, 0, 0, 0, 0, 0], [1, 1, 1, 1, 1, 1]], bool)
+    assert I._max_runs(k) == 3
+    assert I._max_runs(np.ones((4, 4), bool)) == 1
+    assert set(I.METHODS) == set(orf.METHODS)
+    from hydrotools.cuda import _io
+    # /root/reference/src/hydrotools/utils.py:253-265
+    assert _io.infer_nodata("float32") == float(np.finfo("float32").min)
+    assert _io.infer_nodata("uint16") == 65535 and _io.infer_nodata("int8") == -128
+    assert _io.infer_nodata("bool") is False
