@@ -358,12 +358,17 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             }
         }
         else {
-        // ---- general tiles: int32 box, three passes through shared memory
-        for (int i = tid; i < BW * BH; i += THREADS) {
-            const float f = __int_as_float(alt[i]);
-            alt[i] = f == F_INVALID ? INVALID : (int32_t)f;
+        // ---- general tiles: three passes through shared memory.  Cells whose window is
+        // all valid and off the raster border still take the fp32 rule; the integer rule
+        // (seeds, NULL neighbours) runs only next to NULL cells and borders.  The
+        // validating instantiation compares integers (ties) and converts the box first.
+        if (VALIDATE) {
+            for (int i = tid; i < BW * BH; i += THREADS) {
+                const float f = __int_as_float(alt[i]);
+                alt[i] = f == F_INVALID ? INVALID : (int32_t)f;
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
         // ---- pass 1: direction byte of the tile and a 1-cell ring around it
         bool edge_seen = false;
@@ -373,9 +378,31 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             const bool border = yy == yy_top || xx == xx_left || yy == yy_bot || xx == xx_right;
             const int border_code = yy == yy_top ? 2 : xx == xx_left ? 4 : yy == yy_bot ? 6 : 8;
             unsigned pp = 0, tt = 0;
-            const uint8_t b = d8_cell<VALIDATE>(a[-BW - 1], a[-BW], a[-BW + 1], a[-1], a[0], a[1],
-                                                a[BW - 1], a[BW], a[BW + 1], border, border_code,
-                                                p, pp, tt);
+            uint8_t b;
+            if (VALIDATE)
+                b = d8_cell<VALIDATE>(a[-BW - 1], a[-BW], a[-BW + 1], a[-1], a[0], a[1], a[BW - 1],
+                                      a[BW], a[BW + 1], border, border_code, p, pp, tt);
+            else {
+                const float *f = reinterpret_cast<const float *>(a);
+                const float w0 = f[-BW - 1], w1 = f[-BW], w2 = f[-BW + 1], w3 = f[-1], c = f[0],
+                            w5 = f[1], w6 = f[BW - 1], w7 = f[BW], w8 = f[BW + 1];
+                const float mx = fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(fmaxf(w5, w6), fmaxf(w7, w8)));
+                if (c == F_INVALID)
+                    b = HT_DIR_NULL;
+                else if (!border && mx < F_INVALID) {
+                    bool amb;
+                    int code = d8_plain_cell(w0, w1, w2, w3, c, w5, w6, w7, w8, p, amb);
+                    if (amb)
+                        code = d8_exact_cell(w0, w1, w2, w3, c, w5, w6, w7, w8, p.ew, p.ns, p.diag,
+                                             p.inv_ew, p.inv_ns, p.inv_diag);
+                    b = (uint8_t)code;
+                }
+                else {
+                    auto iv = [](float v) -> int32_t { return v == F_INVALID ? INVALID : (int32_t)v; };
+                    b = d8_cell<false>(iv(w0), iv(w1), iv(w2), iv(w3), iv(c), iv(w5), iv(w6), iv(w7),
+                                       iv(w8), border, border_code, p, pp, tt);
+                }
+            }
             dirs[yy * DP + xx + DX0] = b;
             edge_seen |= (b & HT_DIR_EDGE) != 0;
             if (VALIDATE) {
