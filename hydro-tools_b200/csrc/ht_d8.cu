@@ -242,6 +242,7 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[STAGES];
     __shared__ __align__(16) uint8_t dirs[DH * DP];
+    __shared__ __align__(16) uint8_t tmap[DH * DP]; // 1 where a re-pointed seed drains into the cell
     __shared__ int any_edge;
 
     const int tid = threadIdx.x;
@@ -293,6 +294,9 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
 
         // ---- pass 0: float metres -> GRASS integer millimetres (integer-valued
         // floats), in place.  Outside the raster the TMA filled NaN.
+        if (!VALIDATE)
+            for (int i = tid; i < DH * DP / 16; i += THREADS)
+                reinterpret_cast<uint4 *>(tmap)[i] = make_uint4(0u, 0u, 0u, 0u);
         bool saw_invalid = false;
         {
             float4 *box = reinterpret_cast<float4 *>(alt);
@@ -405,6 +409,15 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             }
             dirs[yy * DP + xx + DX0] = b;
             edge_seen |= (b & HT_DIR_EDGE) != 0;
+            if (!VALIDATE && (b & (HT_DIR_EDGE | HT_DIR_NEG | HT_DIR_NULL)) == HT_DIR_EDGE) {
+                // rule R4: the cell an unworked seed is re-pointed at has its accumulation
+                // sign flipped.  The seed tells its receiver (all writers store the same 1).
+                const int code = b & HT_DIR_CODE;
+                const int ty2 = yy + (int)((0x1A900u >> (2 * code)) & 3u) - 1;
+                const int tx2 = xx + (int)((0x29018u >> (2 * code)) & 3u) - 1;
+                if (ty2 >= 0 && ty2 < DH && tx2 >= 0 && tx2 < DW)
+                    tmap[ty2 * DP + tx2 + DX0] = 1;
+            }
             if (VALIDATE) {
                 // only cells of the tile itself are counted
                 const bool own = yy >= 1 && yy <= TH && xx >= 1 && xx <= TW &&
@@ -419,8 +432,7 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
             any_edge = 1;
         __syncthreads();
 
-        // ---- pass 2: taint flag (rule R4: the cell an unworked seed is re-pointed
-        // at has its accumulation sign flipped) and 128-bit row stores
+        // ---- pass 2: taint flags collected in pass 1, 128-bit row stores
         if (!VALIDATE) {
             const bool need_taint = any_edge != 0;
             // item -> 16 consecutive cells of one row (8 items per row).  Rows -1 and
@@ -437,27 +449,8 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
                 const uint8_t *row = dirs + yy * DP + DX0 + 1 + seg * 16; // 16-B aligned
                 uint4 v = *reinterpret_cast<const uint4 *>(row);
                 if (need_taint && own) {
-                    uint32_t out[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const uint8_t b = row[j];
-                        if (b & HT_DIR_NULL)
-                            continue;
-                        bool taint = false;
-#pragma unroll
-                        for (int kk = 0; kk < 9; kk++) {
-                            if (kk == 4)
-                                continue;
-                            const uint8_t u = row[j + (kk / 3 - 1) * DP + (kk % 3 - 1)];
-                            // neighbour at window cell kk points back at me with code
-                            // win2code(8 - kk)
-                            taint |= ((u & (HT_DIR_EDGE | HT_DIR_NEG | HT_DIR_NULL)) == HT_DIR_EDGE) &&
-                                     ((u & HT_DIR_CODE) == win2code(8 - kk));
-                        }
-                        if (taint)
-                            out[j >> 2] |= (uint32_t)HT_DIR_TAINT << (8 * (j & 3));
-                    }
-                    v = make_uint4(out[0], out[1], out[2], out[3]);
+                    const uint4 t = *reinterpret_cast<const uint4 *>(tmap + yy * DP + DX0 + 1 + seg * 16);
+                    v.x |= t.x << 6; v.y |= t.y << 6; v.z |= t.z << 6; v.w |= t.w << 6; // HT_DIR_TAINT
                 }
                 uint8_t *dst = p.packed + lr * p.packed_ld + gc;
                 if (gc + 16 <= p.cols)
