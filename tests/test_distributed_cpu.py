@@ -129,6 +129,66 @@ class OracleBand:
     def results(self):
         return self.fd_out, self.acc
 
+    def dem_view(self):
+        return torch.from_numpy(self.dem[2:2 + self.rows].copy())
+
+
+def _filter_worker(rank, world, port, cuts, kernel, method, q):
+    """BandEngine.window_filter over gloo: the halo rows a window needs come from the
+    neighbour bands; the per-band filter itself is the numpy restatement here."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hydrotools.cuda import distributed as HD
+    from hydrotools.cuda import interpolate as I
+    from oracle import rasterfilter as orf
+
+    def cpu_window_filter(a, k, m, nodata=None, halo_top=0, halo_bot=0):
+        a = a.numpy().astype(np.float32).copy()
+        if nodata is not None:
+            a[a == nodata] = np.nan
+        out = orf.raster_filter(a, k, m)
+        return torch.from_numpy(out[halo_top:a.shape[0] - halo_bot])
+
+    I.window_filter = cpu_window_filter
+    dem = oracle.synth_dem(3, cuts[-1], 97, with_nulls=True)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    band = OracleBand(dem, lo, hi, ND)
+    eng = HD.BandEngine(rank, world, hi - lo, 97, cuts[-1], 10.0, 10.0, ND, band=band)
+    out = eng.window_filter(kernel, method)
+    q.put((rank, out.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cuts,kernel,method", [([0, 60, 130], (5, 3), "mean"),
+                                                ([0, 45, 90, 130], (8, 8), "std"),
+                                                ([0, 30, 130], (1, 9), "max")])
+def test_band_filter_over_gloo(cuts, kernel, method):
+    from oracle import rasterfilter as orf
+    world = len(cuts) - 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500) + world
+    procs = [ctx.Process(target=_filter_worker, args=(r, world, port, cuts, kernel, method, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = dict()
+    for _ in range(world):
+        r, o = q.get(timeout=180)
+        parts[r] = o
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    dem = oracle.synth_dem(3, cuts[-1], 97, with_nulls=True).astype(np.float32)
+    dem[dem == ND] = np.nan
+    exp = orf.raster_filter(dem, kernel, method)
+    got = np.vstack([parts[r] for r in range(world)])
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    m = ~np.isnan(exp)
+    np.testing.assert_array_equal(got[m], exp[m])
+
 
 def _worker(rank, world, port, cuts, seed, flip, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
