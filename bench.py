@@ -172,7 +172,7 @@ def run_product(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import hydrotools.cuda as hc
-    from hydrotools.cuda import _native as N, _device as D, synth, watershed as W
+    from hydrotools.cuda import _native as N, _device as D, synth
     from hydrotools.cuda import distributed as HD
 
     peak, peak_kind = measured_peak()

@@ -5,7 +5,6 @@ fused sm_100a stencil (``ht_terrain_fused_f32``) over a single read of the DEM.
 """
 from typing import Dict, Iterable, Optional
 
-import numpy as np
 import torch
 
 from . import _native as N

@@ -12,7 +12,7 @@ without ``q``, interpolate.py:230-240) and custom numba callables raise
 ``NotImplementedError`` -- there is no CPU fallback.
 """
 import ctypes as C
-from typing import Optional, Tuple, Union
+from typing import Optional, Union
 
 import numpy as np
 import torch
