@@ -117,15 +117,21 @@ def oracle_sample_gcells(sample_rows, cols, total_rows):
 
 def run_reference(args):
     """CPU arm: the oracle restatement of r.watershed -s -a (GRASS is
-    single-threaded; so is this), each step one bounded sample of the workload."""
+    single-threaded; so is this).  `--steps 1 --warmup 0` times ONE pass over the whole
+    configs[1] raster (about a minute, 4 GB); otherwise every step is a bounded row
+    sample of it, and the line says so (`extrapolated`, `sample_rows`, config.rows)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     total_rows = ROWS_PER_GPU * args.gpus
-    # size the sample so that (steps + warmup) samples take about two minutes
-    g, dt = oracle_sample_gcells(500, COLS, total_rows)
-    budget = 120.0 / max(args.steps + args.warmup, 1)
-    rows = int(max(200, min(2500, 500 * budget / max(dt, 1e-3) * 0.8)))
+    full = args.steps == 1 and args.warmup == 0 and args.gpus == 1
+    if full:
+        rows = total_rows
+    else:
+        # size the sample so that (steps + warmup) samples take about two minutes
+        g, dt = oracle_sample_gcells(500, COLS, total_rows)
+        budget = 120.0 / max(args.steps + args.warmup, 1)
+        rows = int(max(200, min(2500, 500 * budget / max(dt, 1e-3) * 0.8)))
     for _ in range(args.warmup):
         oracle_sample_gcells(rows, COLS, total_rows)
     t0 = time.perf_counter()
@@ -133,13 +139,20 @@ def run_reference(args):
         oracle_sample_gcells(rows, COLS, total_rows)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = rows * COLS / dt / 1e9
-    sample = f"first {rows} rows x {COLS} cols of the {total_rows} x {COLS} synthetic DEM per step"
+    sample = (f"the whole {total_rows} x {COLS} synthetic DEM" if full else
+              f"first {rows} rows x {COLS} cols of the {total_rows} x {COLS} synthetic DEM per step")
+    cfg = workload_config(args.gpus)
+    cfg["rows_timed_per_step"] = rows
+    cfg["extrapolated"] = not full
+    if not full:
+        cfg["note"] = (f"CPU arm times a {rows}-row sample per step and reports its per-cell rate; "
+                       "A* is O(N log N) with a growing working set, so the sample flatters the CPU")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg, "extrapolated": not full, "sample_rows": rows,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -154,6 +167,237 @@ def workload_config(n):
         "sharding": "whole raster on one GPU" if n == 1 else f"{n} row bands of {ROWS_PER_GPU} rows",
         "l2": "inputs (400 MB DEM per GPU) exceed the 126 MB L2; no flush between iterations",
     }
+
+
+
+# --------------------------------------------------------------------------- correctness inside the run
+_DR = (0, -1, -1, -1, 0, 1, 1, 1, 0)
+_DC = (0, 1, 0, -1, -1, -1, 0, 1, 1)
+
+
+def mass_balance(fd, fa, rank, world, total_rows, weight=None, watershed_edges=True):
+    """Size-independent check of a sharded accumulation, on the device:
+      * acc(c) == w(c) + sum of acc over c's donors for EVERY cell of every band, the donors
+        in the neighbour band included (edge rows of direction and accumulation travel);
+      * the accumulation of the cells that do not pass flow on adds up to the total weight
+        (the cell count when `weight` is None).
+    `watershed_edges`: r.watershed semantics (border cells keep their flow); otherwise
+    r.flowaccumulation's (a cell passes flow on unless its receiver is outside).
+    Returns (ok_everywhere, terminal_sum, expected_sum)."""
+    import torch
+    import torch.distributed as dist
+    dev = fd.device
+    rows, cols = fd.shape
+    g0 = rank * rows
+    dr = torch.tensor(_DR, device=dev)
+    dc = torch.tensor(_DC, device=dev)
+    cc1 = torch.arange(cols, device=dev).view(1, -1)
+    if world > 1:
+        edge_fd = torch.stack([fd[0], fd[-1]]).contiguous()
+        edge_fa = torch.stack([fa[0], fa[-1]]).contiguous()
+        all_fd = torch.empty((world * 2, cols), dtype=fd.dtype, device=dev)
+        all_fa = torch.empty((world * 2, cols), dtype=fa.dtype, device=dev)
+        dist.all_gather_into_tensor(all_fd, edge_fd)
+        dist.all_gather_into_tensor(all_fa, edge_fa)
+    inflow = torch.zeros((rows, cols), dtype=torch.float64, device=dev)
+
+    def passes(f, grow):
+        f = f.to(torch.int64)
+        rr = grow.expand(-1, cols)
+        cc = cc1.expand(f.shape[0], -1)
+        code = f.clamp(min=0, max=8)
+        tr, tc = rr + dr[code], cc + dc[code]
+        ok = (f > 0) & (f <= 8) & (tr >= 0) & (tr < total_rows) & (tc >= 0) & (tc < cols)
+        if watershed_edges:
+            ok &= ~((rr == 0) | (cc == 0) | (rr == total_rows - 1) | (cc == cols - 1))
+        return ok, tr - g0, tc
+
+    def scatter(f, a, grow):
+        ok, tr, tc = passes(f, grow)
+        ok = ok & (tr >= 0) & (tr < rows)
+        inflow.view(-1).index_add_(0, (tr * cols + tc)[ok], a[ok])
+
+    term = torch.zeros((), dtype=torch.float64, device=dev)
+    CH = 500
+    for r0 in range(0, rows, CH):
+        r1 = min(rows, r0 + CH)
+        grow = torch.arange(g0 + r0, g0 + r1, device=dev).view(-1, 1)
+        ok, _, _ = passes(fd[r0:r1], grow)
+        term += fa[r0:r1][~ok].sum()
+        scatter(fd[r0:r1], fa[r0:r1], grow)
+    if rank > 0:
+        k = 2 * (rank - 1) + 1
+        scatter(all_fd[k:k + 1], all_fa[k:k + 1], torch.tensor([[g0 - 1]], device=dev))
+    if rank < world - 1:
+        k = 2 * (rank + 1)
+        scatter(all_fd[k:k + 1], all_fa[k:k + 1], torch.tensor([[g0 + rows]], device=dev))
+    own = 1.0 if weight is None else weight.double()
+    expect = inflow + own
+    if weight is None:
+        good = torch.equal(fa, expect)
+    else:  # fp64 report of an exact integer sum: one rounding per value
+        good = bool(((fa - expect).abs() <= 1e-9 * expect.abs().clamp(min=1e-300)).all())
+    ok_t = torch.tensor([1.0 if good else 0.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(rows * cols) if weight is None else float(weight.double().sum())],
+                       dtype=torch.float64, device=dev)
+    term = term.reshape(1)
+    if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(term)
+        dist.all_reduce(tot)
+    return bool(ok_t.item()), float(term.item()), float(tot.item())
+
+
+def oracle_parity_small(rank, world, dev):
+    """Oracle comparison inside the run (over NCCL when world > 1): D8 + accumulation
+    (unsigned and signed), weighted accumulation over the stored direction grid, on a side
+    raster small enough for the single-threaded oracle: 700 rows per GPU x 1500 columns,
+    with NULL blobs.  Returns mismatch counts (all must be 0)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from hydrotools.cuda import distributed as HD
+    rows, cols = 700, 1500
+    total = rows * world
+    nd = -32767.0
+    eng = HD.BandEngine(rank, world, rows, cols, total, CSX, CSY, nd)
+    eng.generate_synthetic(5, with_nulls=True)
+    eng.flow_direction_accumulation()
+    fd, fa = (t.clone() for t in eng.results())
+    eng.flow_direction_accumulation(positive_only=False)
+    _, fs = (t.clone() for t in eng.results())
+    import oracle
+    w_all = oracle.synth_weight(5, total, cols)
+    eng.load_direction(fd)
+    wsum = eng.flow_accumulation(torch.from_numpy(w_all[rank * rows:(rank + 1) * rows]).to(dev))
+    cnt = eng.flow_accumulation(None)
+
+    def gather(t):
+        t = t.contiguous()
+        if world == 1:
+            return t.cpu().numpy()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return torch.cat(parts).cpu().numpy()
+
+    got = {k: gather(v) for k, v in (("fd", fd), ("fa", fa), ("fs", fs), ("w", wsum), ("cnt", cnt))}
+    out = None
+    if rank == 0:
+        dem = oracle.synth_dem(5, total, cols, with_nulls=True)
+        efd, efa = oracle.rwatershed(dem, nd, CSX, CSY)
+        _, efs = oracle.rwatershed(dem, nd, CSX, CSY, positive_only=False)
+        ew = oracle.flowacc(efd, w_all)
+        ec = oracle.flowacc(efd)
+
+        def neq(a, b):
+            return int((~((a == b) | (np.isnan(a) & np.isnan(b)))).sum())
+        m = ~np.isnan(ew)
+        rel = float(np.max(np.abs(got["w"][m] - ew[m]) / np.maximum(np.abs(ew[m]), 1e-30)))
+        out = {"raster": f"{total}x{cols} with NULL blobs, {world} band(s) of {rows} rows",
+               "direction_mismatches": int((got["fd"] != efd).sum()),
+               "accumulation_mismatches": neq(got["fa"], efa),
+               "signed_accumulation_mismatches": neq(got["fs"], efs),
+               "stored_direction_count_mismatches": neq(got["cnt"], ec),
+               "weighted_max_rel_err": rel, "weighted_tolerance": 1e-5,
+               "weighted_nan_mask_equal": bool(np.array_equal(np.isnan(got["w"]), np.isnan(ew))),
+               "oracle": "oracle.rwatershed / oracle.flowacc on the whole raster, rank 0"}
+        out["ok"] = (out["direction_mismatches"] == 0 and out["accumulation_mismatches"] == 0 and
+                     out["signed_accumulation_mismatches"] == 0 and
+                     out["stored_direction_count_mismatches"] == 0 and rel <= 1e-5 and
+                     out["weighted_nan_mask_equal"])
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def weighted_run(rank, world, rows, cols, peak, barrier, dev, steps=3):
+    """Row a3 (FlowAccumulation.calculate "sum", watershed.py:357-382): weighted accumulation
+    over a STORED direction grid (r.flowaccumulation semantics), weights ~ U(1650, 1700) mm.
+    Timed: weight maximum (+ 4-byte all-reduce), stages A / B / C and the band exchange."""
+    import torch
+    import torch.distributed as dist
+    from hydrotools.cuda import distributed as HD, _native as N, _device as D
+    total = rows * world
+    eng = HD.BandEngine(rank, world, rows, cols, total, CSX, CSY)
+    eng.generate_synthetic(SEED)
+    eng.flow_direction_accumulation()
+    fd = eng.results()[0].clone()
+    eng.load_direction(fd)
+    w, wld = D.empty_padded(rows, cols, torch.float32, dev, 4)
+    N.call("ht_synth_weight_f32", w.data_ptr(), rows, cols, wld, SEED + 1, rank * rows, D.stream_ptr())
+    wv = w[:, :cols]
+    for _ in range(2):
+        acc = eng.flow_accumulation(wv)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        acc = eng.flow_accumulation(wv)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    again = eng.flow_accumulation(wv)
+    rep = torch.tensor([1.0 if torch.equal(again, acc) else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rep, op=dist.ReduceOp.MIN)
+    ok, term, tot = mass_balance(fd, acc, rank, world, total, weight=wv, watershed_edges=False)
+    del eng, acc, again, w
+    torch.cuda.empty_cache()
+    cells = total * cols
+    gbs = rows * cols * 13 / (ms * 1e-3) / 1e9
+    return {"workload": f"{total}x{cols} fp32 weights over a stored int8 direction grid, {world} band(s)",
+            "ms": ms, "gcells_s": cells / (ms * 1e-3) / 1e9, "algorithmic_bytes_per_cell": 13,
+            "achieved": gbs, "peak": peak, "unit": "GB/s per GPU", "frac": gbs / peak,
+            "lower_bound_ms": rows * cols * 13 / (peak * 1e9) * 1e3,
+            "bit_reproducible": bool(rep.item()),
+            "parity": {"acc_equals_weight_plus_donors_everywhere": ok,
+                       "terminal_weight": term, "total_weight": tot,
+                       "rel_diff": abs(term - tot) / max(abs(tot), 1e-300)}}
+
+
+def count_run(rank, world, rows, cols, peak, barrier, dev, steps=3):
+    """D8 + cell-count accumulation on rows x cols per GPU (BASELINE.json configs[4] when
+    8 x 12 500 x 100 000), checked by mass balance on every cell."""
+    import torch
+    import torch.distributed as dist
+    from hydrotools.cuda import distributed as HD
+    total = rows * world
+    eng = HD.BandEngine(rank, world, rows, cols, total, CSX, CSY)
+    eng.generate_synthetic(SEED)
+    pits, ties = eng.validate()
+    for _ in range(2):
+        eng.flow_direction_accumulation()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.flow_direction_accumulation()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    fd, fa = eng.results()
+    ok, term, tot = mass_balance(fd, fa, rank, world, total)
+    mem = torch.tensor([torch.cuda.max_memory_allocated() / 2**30], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+    del eng, fd, fa
+    torch.cuda.empty_cache()
+    cells = total * cols
+    gbs = rows * cols * 14 / (ms * 1e-3) / 1e9
+    return {"workload": f"{total}x{cols} fp32 DEM, D8 + cell-count accumulation, {world} band(s) of {rows} rows",
+            "validate": {"pits": pits, "ties": ties},
+            "ms": ms, "gcells_s": cells / (ms * 1e-3) / 1e9, "algorithmic_bytes_per_cell": 14,
+            "achieved": gbs, "peak": peak, "unit": "GB/s per GPU", "frac": gbs / peak,
+            "lower_bound_ms": rows * cols * 14 / (peak * 1e9) * 1e3,
+            "peak_gib_per_gpu": float(mem.item()),
+            "parity": {"acc_equals_one_plus_donors_everywhere": ok, "terminal_cells": term,
+                       "cells": tot, "exact": ok and term == tot}}
 
 
 # --------------------------------------------------------------------------- product arm
@@ -297,11 +541,27 @@ def run_product(args):
     path_roofline = {"algorithmic_bytes_per_cell": 14, "achieved": path_gbs, "peak": peak,
                      "unit": "GB/s", "frac": path_gbs / peak}
 
+    # correctness of THIS run's result: acc == 1 + donors on every cell of every band
+    # (neighbour-band donors included) and terminal mass == cells
+    fd_dev, fa_dev = engine.results()
+    mb_ok, mb_term, mb_tot = mass_balance(fd_dev, fa_dev, rank, world, total_rows)
+    parity = {"bench_raster": {"acc_equals_one_plus_donors_everywhere": mb_ok,
+                               "terminal_cells": mb_term, "cells": mb_tot,
+                               "exact": mb_ok and mb_term == mb_tot}}
+
     cpu = None
     # configs[2]: fused slope + aspect + TRI on 32768^2; with N > 1 the same raster in N
     # row bands (strong scaling), halo rows exchanged inside the timed region
-    del engine
+    del engine, fd_dev, fa_dev
     torch.cuda.empty_cache()
+    parity["oracle"] = oracle_parity_small(rank, world, dev)
+    # row a3 on the bench raster (single GPU) / per band
+    weighted = weighted_run(rank, world, rows, cols, peak, barrier, dev)
+    targets = None
+    if world == 8:
+        # BASELINE.json configs[4] (north_star target) and configs[3]
+        targets = {"configs[4]": count_run(rank, world, 12500, 100000, peak, barrier, dev),
+                   "configs[3]": weighted_run(rank, world, 5000, 40000, peak, barrier, dev)}
     stencil = terrain_roofline(peak) if world == 1 else terrain_bands(peak, rank, world, barrier, dev)
     wfilter = window_filter_bench(peak) if world == 1 else None
     if rank == 0:
@@ -310,6 +570,7 @@ def run_product(args):
         cpu = {"value": g, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first 2500 rows x {COLS} cols of the same DEM, oracle/rwatershed.c "
                          f"(restatement of single-threaded GRASS r.watershed -s -a), {dt:.1f} s",
+               "sample_rows": 2500, "extrapolated": True,
                "host_cores_available": os.cpu_count()}
 
     if rank == 0:
@@ -322,6 +583,7 @@ def run_product(args):
             "roofline": roofline, "path_roofline": path_roofline, "kernels": kernels,
             "boundary_graph": {"resolve_rounds": resolve_rounds,
                                "note": "pointer-doubling rounds of stage B until no node is active"},
+            "parity": parity, "weighted": weighted, "target_configs": targets,
             "stencil_roofline": stencil, "window_filter": wfilter,
             "cpu_baseline": cpu,
         }))
@@ -429,16 +691,25 @@ def window_filter_bench(peak):
 def terrain_cpu_baseline(n):
     """gdaldem is single-threaded and the reference runs it three times (slope, aspect,
     TRI: elevation.py:41-54, 70-78, 118-126); the oracle restatement computes the three
-    in one pass, on a bounded row sample of the same DEM, one core."""
+    in one pass, on a bounded row sample of the same DEM: one core (what gdaldem uses) and
+    all host cores (rows split over pthreads)."""
     import oracle
-    rows = 1024
+    rows = 2048
     dem = oracle.synth_dem(SEED, rows, n, row0=0, total_rows=n)
+    oracle.gdaldem(dem[:64], None, CSX, CSY)
     t0 = time.perf_counter()
-    oracle.gdaldem(dem, None, CSX, CSY)
-    dt = time.perf_counter() - t0
-    return {"value": rows * n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+    oracle.gdaldem(dem, None, CSX, CSY, threads=1)
+    dt1 = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    oracle.gdaldem(dem, None, CSX, CSY, threads=cores)
+    dtn = time.perf_counter() - t0
+    return {"value": rows * n / dt1 / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"first {rows} rows x {n} cols, oracle/gdaldem.c (slope + aspect + TRI in one "
-                      f"pass; the reference spawns gdaldem once per output), {dt:.1f} s"}
+                      f"pass; the reference spawns gdaldem once per output), {dt1:.1f} s",
+            "sample_rows": rows, "extrapolated": True,
+            "all_cores": {"value": rows * n / dtn / 1e9, "unit": UNIT, "cores": cores,
+                          "kind": "port", "sample": f"same sample, rows split over {cores} threads, {dtn:.2f} s"}}
 
 
 def terrain_bands(peak, rank, world, barrier, dev):

@@ -64,6 +64,10 @@ struct AccArgs {
     int64_t lacc_ld;
     const uint8_t *packed;    // owned row 0 of the packed grid (rare global look-ups)
     int64_t packed_ld;
+    long long *lacc64;        // weighted mode: tile-local sums in the tile's unit, stage A -> C
+    int64_t lacc64_ld;
+    int32_t *tile_e;          // weighted mode: log2(tile unit / global unit) per tile
+    const unsigned *gmax_bits; // weighted mode: bits of the raster's largest |weight| (float)
 };
 
 // row / column step of GRASS code 1..8 (2-bit tables: dr+1 = 0,0,0,1,2,2,2,1; dc+1 = 2,1,0,0,0,1,2,2)
@@ -86,9 +90,55 @@ __device__ __forceinline__ bool perimeter_cell(int k, int th, int tw, int &ly, i
 
 static_assert(SLOTS == THREADS, "one perimeter slot per thread");
 
+// 128-bit two's complement integer: weighted sums are carried as exact fixed point
+// (order-independent, hence bit-reproducible; see "Weighted mode" below).
+struct i128 {
+    unsigned long long lo;
+    long long hi;
+    __host__ __device__ i128() {}
+    __host__ __device__ i128(int v) : lo((unsigned long long)(long long)v), hi(v < 0 ? -1ll : 0ll) {}
+    __host__ __device__ i128(unsigned long long l, long long h) : lo(l), hi(h) {}
+};
+__host__ __device__ __forceinline__ i128 operator+(const i128 &a, const i128 &b)
+{
+    i128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ll : 0ll);
+    return r;
+}
+__host__ __device__ __forceinline__ i128 &operator+=(i128 &a, const i128 &b) { a = a + b; return a; }
+__host__ __device__ __forceinline__ bool operator!=(const i128 &a, const i128 &b) { return a.lo != b.lo || a.hi != b.hi; }
+// v << e, 0 <= e < 64, v sign-extended to 128 bits
+__device__ __forceinline__ i128 shl_i64(long long v, int e)
+{
+    i128 r;
+    r.lo = (unsigned long long)v << e;
+    r.hi = e ? (v >> (64 - e)) : (v < 0 ? -1ll : 0ll);
+    return r;
+}
+__device__ __forceinline__ double i128_to_double(const i128 &v)
+{
+    // hi * 2^64 + lo: both terms exact or correctly rounded, one more rounding in the sum
+    return (double)v.hi * 18446744073709551616.0 + (double)v.lo;
+}
+
 template <typename V> __device__ __forceinline__ void atomic_add_v(V *p, V v);
 template <> __device__ __forceinline__ void atomic_add_v<unsigned long long>(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 template <> __device__ __forceinline__ void atomic_add_v<double>(double *p, double v) { atomicAdd(p, v); }
+// two native 64-bit atomics with the carry handed on: the final 128-bit value does not
+// depend on the order of the adds (owners read it only after a grid barrier / kernel end)
+template <> __device__ __forceinline__ void atomic_add_v<i128>(i128 *p, i128 v)
+{
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(p);
+    unsigned long long carry = 0ull;
+    if (v.lo) {
+        const unsigned long long old = atomicAdd(w, v.lo);
+        carry = (old + v.lo) < old ? 1ull : 0ull;
+    }
+    const unsigned long long h = (unsigned long long)v.hi + carry;
+    if (h)
+        atomicAdd(w + 1, h);
+}
 
 // ===========================================================================
 // Count modes (cell counts, taint counts): lean integer kernels.
@@ -317,32 +367,92 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 }
 
 // ---------------------------------------------------------------------------
-// Weighted mode (fp32 weights, fp64 sums): the same pointer doubling with double
-// sums and shared fp64 atomics.  Stage C is stage A again with the resolved inflow
-// of the entry slots arriving as initial sums -- no tile-local hand-over (it would
-// cost 8 B per cell), no walkers.  The order of the atomic adds is not fixed, so
-// results agree from run to run to ~1e-15 relative, far inside the 1e-5 contract.
+// Weighted mode (fp32 weights, sums reported as fp64): EXACT FIXED POINT.
+// Shared-memory fp64 (and 64-bit integer) atomicAdd is a compare-and-swap loop on
+// sm_100a (SASS ATOMS.CAST.SPIN.64); 32-bit integer adds are native (ATOMS.ADD).  So
+// the weights are quantised once and every sum downstream is integer arithmetic:
+//   * global unit 2^-sg, sg = G_BITS - ilogb(largest |weight| of the raster): the
+//     largest weight is ~2^61 units, a sum over 2^34 cells still fits 128 bits;
+//   * stage A works in a per-tile unit 2^(et - sg), et >= 0 chosen so that the tile's
+//     largest weight is < 2^Q_BITS units: tile-local sums fit 64 bits and live in
+//     shared memory as two 32-bit words (native atomic add, carry handed on);
+//   * flow that leaves a tile, the boundary graph (stage B) and stage C are 128-bit
+//     integers in the global unit (two native 64-bit global atomics with carry).
+// Integer addition is associative, so the result does not depend on the order of the
+// atomics: weighted accumulation is bit-reproducible from run to run.  Quantisation
+// error per weight <= 2^-(Q_BITS+1) of the tile's largest weight (and nothing for
+// weights within 2^Q_BITS of the raster's largest); the contract is 1e-5 relative.
+// Stage A leaves the tile-local sums (int64, 8 B/cell) for stage C, which adds the
+// resolved inflow along the entry paths with walkers, like the count mode.
 // ---------------------------------------------------------------------------
-constexpr int SMD_PTR = SM_EFF;                  // uint16[T*T] pointer entries
-constexpr int SMD_ARR = SMD_PTR + T * T * 2;     // double[T*T] sums that arrived at a cell
-constexpr int SMD_LUT = SMD_ARR + T * T * 8;     // uint32[16] code -> pointer step | active
-constexpr int SMD_BAR = SMD_LUT + 64;
-constexpr int SMD_TOTAL = SMD_BAR + 32;
-static_assert(SMD_ARR % 8 == 0, "fp64 array alignment");
+constexpr int Q_BITS = 48;
+constexpr int G_BITS = 61;
 
-template <bool FINAL>
-__global__ void __launch_bounds__(THREADS, 2)
-acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
+__device__ __forceinline__ int scale_exp_of(unsigned gmax_bits)
+{
+    const float g = __uint_as_float(gmax_bits);
+    return g > 0.0f ? G_BITS - ilogbf(g) : 0;
+}
+__device__ __forceinline__ double pow2d(int e) // -1022 <= e <= 1023
+{
+    return __longlong_as_double((long long)(1023 + e) << 52);
+}
+// nodata, NaN and +-inf weigh nothing
+__device__ __forceinline__ float clean_weight(float w, int has_wnd, float wnd)
+{
+    return ((has_wnd && w == wnd) || !(fabsf(w) <= 3.4028234e38f)) ? 0.0f : w;
+}
+
+__global__ void __launch_bounds__(256)
+weight_max_kernel(const float *w, int64_t w_ld, int64_t rows, int64_t cols, int has_wnd, float wnd,
+                  unsigned *out_bits)
+{
+    float m = 0.0f;
+    const int64_t n = rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        m = fmaxf(m, fabsf(clean_weight(w[r * w_ld + c], has_wnd, wnd)));
+    }
+    const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m)); // |x| bits order like x
+    if ((threadIdx.x & 31) == 0 && wm)
+        atomicMax(out_bits, wm);
+}
+
+// 64-bit add into two 32-bit shared words
+__device__ __forceinline__ void smem_add64(uint32_t *lo, uint32_t *hi, long long v)
+{
+    const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)((unsigned long long)v >> 32);
+    uint32_t carry = 0u;
+    if (vlo) {
+        const uint32_t old = atomicAdd(lo, vlo);
+        carry = (uint32_t)(old + vlo) < old ? 1u : 0u;
+    }
+    const uint32_t h = vhi + carry;
+    if (h)
+        atomicAdd(hi, h);
+}
+
+constexpr int SMW_PTR = SM_EFF;                  // uint16[T*T] pointer entries
+constexpr int SMW_LO = SMW_PTR + T * T * 2;      // uint32[T*T] low words of the sums
+constexpr int SMW_HI = SMW_LO + T * T * 4;       // uint32[T*T] high words
+constexpr int SMW_LUT = SMW_HI + T * T * 4;      // uint32[16] code -> pointer step | active
+constexpr int SMW_BAR = SMW_LUT + 64;            // mbarrier, counters, tile maximum
+constexpr int SMW_TOTAL = SMW_BAR + 32;
+
+__global__ void __launch_bounds__(THREADS, 3)
+acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *pk = smem_raw;
-    unsigned char *ptrb = smem_raw + SMD_PTR;   // uint16[T*T]
-    unsigned char *arrb = smem_raw + SMD_ARR;   // double[T*T]
+    unsigned char *ptrb = smem_raw + SMW_PTR;
     uint16_t *ptr16 = reinterpret_cast<uint16_t *>(ptrb);
-    double *arr = reinterpret_cast<double *>(arrb);
-    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMD_LUT);
-    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMD_BAR);
-    int *ctl = reinterpret_cast<int *>(smem_raw + SMD_BAR + 8); // [0] entries of the tile, [1] their place in the list
+    uint32_t *alo = reinterpret_cast<uint32_t *>(smem_raw + SMW_LO);
+    uint32_t *ahi = reinterpret_cast<uint32_t *>(smem_raw + SMW_HI);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMW_LUT);
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMW_BAR);
+    int *ctl = reinterpret_cast<int *>(smem_raw + SMW_BAR + 8); // [0] entries, [1] their place in the list
+    unsigned *tmaxb = reinterpret_cast<unsigned *>(smem_raw + SMW_BAR + 16);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -350,74 +460,72 @@ acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
     if (tid == 0) {
         ctl[0] = 0;
+        *tmaxb = 0u;
         ht::mbar_init(&bar, 1);
         ht::fence_mbar_init();
         ht::mbar_expect_tx(&bar, RH * RP);
         ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
     }
-    if (tid < 16) // added to 2 * (cell index); codes 0, 9..15 never link
+    if (tid < 16)
         lut[tid] = link_offset_of(tid) ? (unsigned)(link_offset_of(tid) * 2) + J_ACTIVE : 0u;
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
-    // thread -> cells tid + 256 k: one column, every 4th row.  A warp covers 32
-    // consecutive cells of a row in every step (conflict-free own accesses).
     const int lx = tid & (T - 1), ly0 = tid >> 6;
+    // the thread's weights while the TMA is in flight
+    float wv[CPT];
 #pragma unroll
-    for (int k = 0; k < CPT; k++)
-        arr[tid + k * THREADS] = 0.0;
-    __syncthreads();
-    if (FINAL) { // resolved inflow of the tile's entry slots arrives like any other donor's sum
-        int ly, plx;
-        if (perimeter_cell(tid, th, tw, ly, plx))
-            arr[ly * T + plx] = reinterpret_cast<const double *>(p.inflow)[(int64_t)tile * SLOTS + tid];
+    for (int k = 0; k < CPT; k++) {
+        const int ly = ly0 + 4 * k;
+        wv[k] = (lx < tw && ly < th) ? clean_weight(p.w[(y0 + ly) * p.w_ld + x0 + lx], p.has_wnd, p.wnd) : 0.0f;
     }
+    __syncthreads();
     ht::mbar_wait(&bar, 0);
 
-    // ---- per cell: low = pointer entry, a = sum to hand on, own = the cell's own value
     unsigned low[CPT];
-    double a[CPT];
-    float own[CPT]; // the cells' own weights (0 where NULL / nodata)
     {
-        // codes that do not link from this column; bit 15: outside the raster; bit 0: code 0
         const unsigned cm = (lx == 0 ? EX_W : 0u) | (lx == tw - 1 ? EX_E : 0u) | (lx >= tw ? 0xFFFFu : 0u) | 1u;
+        float m = 0.0f;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             const int ly = ly0 + 4 * k;
             const unsigned b = pk[(ly + 1) * RP + XO + lx];
             const unsigned ex = cm | (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u) | (ly >= th ? 0xFFFFu : 0u);
             const unsigned code = b & HT_DIR_CODE;
-            // no link: a stop flag, or the receiver is outside the tile / the raster
             const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
-            const bool valid = !(b & HT_DIR_NULL) && !(ex >> 15);
-            float wv = 0.0f;
-            if (valid) {
-                wv = p.w[(y0 + ly) * p.w_ld + x0 + lx];
-                if ((p.has_wnd && wv == p.wnd) || wv != wv)
-                    wv = 0.0f;
-            }
-            own[k] = wv;
+            if (b & HT_DIR_NULL)
+                wv[k] = 0.0f;
+            m = fmaxf(m, fabsf(wv[k]));
             low[k] = 2u * (unsigned)(tid + k * THREADS) + (stop ? 0u : lut[code]);
             ptr16[tid + k * THREADS] = (uint16_t)low[k];
         }
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        if (lane == 0 && wm)
+            atomicMax(tmaxb, wm);
     }
     __syncthreads();
+    // per-tile unit: the tile's largest weight is < 2^Q_BITS units
+    const int sg = scale_exp_of(*p.gmax_bits);
+    const float tmax = __uint_as_float(*tmaxb);
+    const int et = tmax > 0.0f ? max(0, ilogbf(tmax) + 1 + sg - Q_BITS) : 0;
+    const double sc = pow2d(sg - et);
+    long long a[CPT];
 #pragma unroll
-    for (int k = 0; k < CPT; k++)
-        a[k] = (double)own[k] + arr[tid + k * THREADS]; // arr: the inflow (FINAL) or 0
+    for (int k = 0; k < CPT; k++) {
+        a[k] = __double2ll_rn((double)wv[k] * sc);
+        alo[tid + k * THREADS] = (uint32_t)a[k];
+        ahi[tid + k * THREADS] = (uint32_t)((unsigned long long)a[k] >> 32);
+    }
     __syncthreads();
 
-    // ---- pointer doubling.  Only the pointer entries live in shared memory (they are
-    // what other cells read); sums arrive in arr[] and are snapshot into registers.
+    // ---- pointer doubling (as in acc_local_cnt_kernel); the sums include the cell's own weight
     for (int round = 0; round < MAX_ROUNDS; round++) {
-        unsigned was = 0; // cells that were active in this round
+        unsigned was = 0;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             if (low[k] & J_ACTIVE) {
                 const unsigned t2 = low[k] & J_PTR; // 2 * (cell 2^k steps downstream)
                 const unsigned wt = *reinterpret_cast<const uint16_t *>(ptrb + t2);
-                if (a[k] != 0.0)
-                    atomicAdd(reinterpret_cast<double *>(arrb + 4 * t2), a[k]);
-                // t still active: its pointer is 2^(k+1) steps from me; else I am done and
-                // keep the root of the path (t's pointer; a root points at itself)
+                if (a[k])
+                    smem_add64(alo + (t2 >> 1), ahi + (t2 >> 1), a[k]);
                 low[k] = wt;
                 was |= 1u << k;
             }
@@ -429,7 +537,7 @@ acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             if ((was >> k) & 1u) {
                 ptr16[tid + k * THREADS] = (uint16_t)low[k];
                 if (low[k] & J_ACTIVE) {
-                    a[k] = (double)own[k] + arr[tid + k * THREADS];
+                    a[k] = (long long)(((unsigned long long)ahi[tid + k * THREADS] << 32) | alo[tid + k * THREADS]);
                     still = true;
                 }
             }
@@ -438,39 +546,18 @@ acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             break;
     }
 
-    if (FINAL) {
-        // ---- outputs: fp64 sums, NaN where NULL
-        if (p.acc && lx < tw) {
-            double *dst = p.acc + (y0 + ly0) * p.acc_ld + x0 + lx;
-#pragma unroll
-            for (int k = 0; k < CPT; k++, dst += 4 * p.acc_ld) {
-                const int ly = ly0 + 4 * k;
-                if (ly >= th)
-                    break;
-                const bool null = pk[(ly + 1) * RP + XO + lx] & HT_DIR_NULL;
-                *dst = null ? __longlong_as_double(0x7ff8000000000000LL)
-                            : (double)own[k] + arr[tid + k * THREADS];
-            }
-        }
-        return;
-    }
-
     // ---- boundary graph.  thread -> one perimeter slot
     {
         int ly = 0, plx = 0;
         const bool per = perimeter_cell(tid, th, tw, ly, plx);
         const unsigned b = per ? pk[(ly + 1) * RP + plx + XO] : (unsigned)HT_DIR_NULL;
-        // flow that leaves the tile through this cell
         if (per && leaves_tile(b, ly, plx, th, tw)) {
-            float self = p.w[(y0 + ly) * p.w_ld + x0 + plx];
-            if ((p.has_wnd && self == p.wnd) || self != self)
-                self = 0.0f;
-            const double val = (double)self + arr[ly * T + plx];
-            if (val != 0.0)
-                atomicAdd(reinterpret_cast<double *>(p.base) +
-                              exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE)), val);
+            const long long val = (long long)(((unsigned long long)ahi[ly * T + plx] << 32) | alo[ly * T + plx]);
+            if (val)
+                atomic_add_v(reinterpret_cast<i128 *>(p.base) +
+                                 exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE)),
+                             shl_i64(val, et));
         }
-        // entry cell: a cell outside the tile drains into it
         bool entry = false;
         if (per && !(b & HT_DIR_NULL)) {
             const int yy = ly + 1, xx = plx + XO;
@@ -495,7 +582,6 @@ acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             ctl[1] = atomicAdd(p.nlist, ctl[0]);
         __syncthreads();
         if (entry) {
-            // where the path that enters here leaves the tile: the root of the cell
             const int rc = (int)(ptr16[ly * T + plx] >> 1), cy = rc >> 6, cx = rc & (T - 1);
             const unsigned rb = pk[(cy + 1) * RP + cx + XO];
             const int32_t slot = tile * SLOTS + tid;
@@ -506,13 +592,165 @@ acc_f64_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         }
     }
 
+    // ---- tile-local sums (tile unit) and the tile's unit for stage C
+    if (tid == 0)
+        p.tile_e[tile] = et;
+    if (lx < tw) {
+        long long *dst = p.lacc64 + (y0 + ly0) * p.lacc64_ld + x0 + lx;
+        const int64_t step = 4 * p.lacc64_ld;
+#pragma unroll
+        for (int k = 0; k < CPT; k++, dst += step)
+            if (ly0 + 4 * k < th)
+                *dst = (long long)(((unsigned long long)ahi[tid + k * THREADS] << 32) | alo[tid + k * THREADS]);
+    }
+}
+
+// stage C, weighted: final = tile-local sum (shifted to the global unit) + the resolved
+// inflow of every entry upstream, added along the entry's path by a walker.  Cells are
+// four 32-bit word planes in shared memory (128-bit integers, native 32-bit atomic adds
+// with the carry handed on).
+constexpr int WP = T + 4;                       // plane row pitch in words (see CP below)
+constexpr int SMX_W = T * T;                    // after the 64 x 64 packed tile
+constexpr int SMX_BAR = SMX_W + 4 * T * WP * 4;
+constexpr int SMX_TOTAL = SMX_BAR + 16;
+
+__global__ void __launch_bounds__(THREADS, 3)
+acc_final_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *pk = smem_raw; // 64 x 64, no ring
+    uint32_t *wpl = reinterpret_cast<uint32_t *>(smem_raw + SMX_W); // [4][T * WP]
+    uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMX_BAR);
+    constexpr int PLANE = T * WP;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
+    if (tid == 0) {
+        ht::mbar_init(&bar, 1);
+        ht::fence_mbar_init();
+        ht::mbar_expect_tx(&bar, T * T);
+        ht::tma_load_2d(pk, &map, (int)x0, (int)y0 + p.halo_top, &bar);
+    }
+    const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
+    const int q4 = 4 * (tid & 15), r0 = tid >> 4;
+    const int cbase = r0 * WP + q4;
+    const bool wide = q4 + 3 < tw;
+    const int et = p.tile_e[tile];
+    const int sg = scale_exp_of(*p.gmax_bits);
+
+    // tile-local sums -> 128-bit words in the global unit
+    {
+        const long long *src = p.lacc64 + (y0 + r0) * p.lacc64_ld + x0 + q4;
+        const int64_t step = 16 * p.lacc64_ld;
+#pragma unroll
+        for (int i = 0; i < 4; i++, src += step) {
+            long long v[4] = {0ll, 0ll, 0ll, 0ll};
+            if (r0 + 16 * i < th && q4 < tw) {
+                if (wide) {
+                    const longlong2 u0 = *reinterpret_cast<const longlong2 *>(src);
+                    const longlong2 u1 = *reinterpret_cast<const longlong2 *>(src + 2);
+                    v[0] = u0.x; v[1] = u0.y; v[2] = u1.x; v[3] = u1.y;
+                }
+                else
+                    for (int j = 0; j < 4 && q4 + j < tw; j++)
+                        v[j] = src[j];
+            }
+            uint32_t wd[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const i128 g = shl_i64(v[j], et);
+                wd[0][j] = (uint32_t)g.lo; wd[1][j] = (uint32_t)(g.lo >> 32);
+                wd[2][j] = (uint32_t)g.hi; wd[3][j] = (uint32_t)((unsigned long long)g.hi >> 32);
+            }
+#pragma unroll
+            for (int pl = 0; pl < 4; pl++)
+                *reinterpret_cast<uint4 *>(wpl + pl * PLANE + cbase + i * 16 * WP) =
+                    make_uint4(wd[pl][0], wd[pl][1], wd[pl][2], wd[pl][3]);
+        }
+    }
+    int ely = 0, elx = 0;
+    i128 inflow(0);
+    if (perimeter_cell(tid, th, tw, ely, elx))
+        inflow = reinterpret_cast<const i128 *>(p.inflow)[(int64_t)tile * SLOTS + tid];
+    __syncthreads();
+    ht::mbar_wait(&bar, 0);
+
+    // ---- walkers: one per entry cell with inflow
+    if (inflow != i128(0)) {
+        const uint32_t v[4] = {(uint32_t)inflow.lo, (uint32_t)(inflow.lo >> 32), (uint32_t)inflow.hi,
+                               (uint32_t)((unsigned long long)inflow.hi >> 32)};
+        int ly = ely, lx = elx;
+        for (int step = 0; step < T * T; step++) { // the bound only matters for a cyclic raster
+            uint32_t *cell = wpl + ly * WP + lx;
+            uint32_t carry = 0u;
+#pragma unroll
+            for (int pl = 0; pl < 4; pl++) {
+                const uint32_t add = v[pl] + carry;
+                if (carry && add == 0u)
+                    continue; // v[pl] = 0xFFFFFFFF: the carry runs on
+                carry = 0u;
+                if (add) {
+                    const uint32_t old = atomicAdd(cell + pl * PLANE, add);
+                    carry = (uint32_t)(old + add) < old ? 1u : 0u;
+                }
+            }
+            const unsigned b = pk[ly * T + lx];
+            if (!b || leaves_tile(b, ly, lx, th, tw) || (b & FLAGS_STOP))
+                break;
+            const int code = (int)(b & HT_DIR_CODE);
+            if (!link_offset_of(code))
+                break;
+            ly += code_dr(code);
+            lx += code_dc(code);
+        }
+    }
+    __syncthreads();
+
+    // ---- outputs: 4 cells per thread and pass, NaN where NULL
+    if (!p.acc)
+        return;
+    const double unit = pow2d(-sg);
+    double *accp = p.acc + (y0 + r0) * p.acc_ld + x0 + q4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int ly = r0 + 16 * i;
+        if (ly >= th || q4 >= tw)
+            break;
+        uint4 w4[4];
+#pragma unroll
+        for (int pl = 0; pl < 4; pl++)
+            w4[pl] = *reinterpret_cast<const uint4 *>(wpl + pl * PLANE + cbase + i * 16 * WP);
+        const unsigned wq = *reinterpret_cast<const unsigned *>(pk + ly * T + q4);
+        const uint32_t *w0 = reinterpret_cast<const uint32_t *>(&w4[0]);
+        const uint32_t *w1 = reinterpret_cast<const uint32_t *>(&w4[1]);
+        const uint32_t *w2 = reinterpret_cast<const uint32_t *>(&w4[2]);
+        const uint32_t *w3 = reinterpret_cast<const uint32_t *>(&w4[3]);
+        double a[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool null = (wq >> (8 * j)) & HT_DIR_NULL;
+            const i128 g(((unsigned long long)w1[j] << 32) | w0[j],
+                         (long long)(((unsigned long long)w3[j] << 32) | w2[j]));
+            a[j] = null ? __longlong_as_double(0x7ff8000000000000LL) : i128_to_double(g) * unit;
+        }
+        double *dst = accp + (int64_t)(16 * i) * p.acc_ld;
+        if (wide && !(((uintptr_t)dst) & 15)) {
+            reinterpret_cast<double2 *>(dst)[0] = make_double2(a[0], a[1]);
+            reinterpret_cast<double2 *>(dst)[1] = make_double2(a[2], a[3]);
+        }
+        else
+            for (int j = 0; j < 4 && q4 + j < tw; j++)
+                dst[j] = a[j];
+    }
 }
 
 // stage C cell words: lo32 = [31:24] signed receiver offset inside the tile (0 =
 // none) | [23:0] low part of the count; hi32 = count >> 16.  A walker adds its
 // inflow split 16 / rest, so the low field never carries into the offset
-// (<= 256 walkers x 65535 + 4096 < 2^24), and the atomic that adds the low part
-// returns the link to follow.
+// (at most 252 walkers -- one per perimeter cell -- x 65535 + 4096 < 2^24), and the
+// atomic that adds the low part returns the link to follow.
 // Rows of the two count arrays are CP = 68 words apart: with a pitch of 64 every cell
 // of the tile's first / last column falls into one bank, and the walkers that start
 // there (one lane per perimeter cell, moving in step along parallel paths) would
@@ -728,12 +966,16 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch)
 // at the start of round k + 1 (nobody writes that buffer then) -- one grid
 // barrier per round.  A node whose pointer has run off the end of its path is
 // done; what still arrives for it stays in arr[] and is added at the very end.
-constexpr int MARK_SHIFT = 48; // band-edge marks ride in bits 48.. of the u64 sums
+// band-edge marks ride in bits 40.. of the u64 sums: counts stay below 2^40 (rasters of up to
+// 10^12 cells), and the 24-bit mark field sums up to 16.7 M marked slots upstream of a node
+// (a band has 2 * cols of them) without wrapping to zero
+constexpr int MARK_SHIFT = 40;
 __device__ __forceinline__ unsigned long long masked_plus(unsigned long long old, unsigned long long add)
 {
     return (old & ((1ull << MARK_SHIFT) - 1ull)) + add;
 }
 __device__ __forceinline__ double masked_plus(double old, double add) { return old + add; }
+__device__ __forceinline__ i128 masked_plus(const i128 &old, const i128 &add) { return old + add; }
 
 template <typename V>
 __global__ void __launch_bounds__(256, 4)
@@ -823,7 +1065,7 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
         const int64_t u = list ? list[i] : i;
         const V total = a[i] + arr0[i] + arr1[i];
         // delta resolve: the totals are a correction on top of an earlier result whose
-        // upper 16 bits carried band-edge marks (u64 values only)
+        // upper 24 bits carried band-edge marks (u64 values only)
         agg_out[u] = add_to_masked ? masked_plus(agg_out[u], total) : total;
         if (rootA && root_out)
             root_out[u] = list ? list[rootA[i]] : rootA[i];
@@ -939,15 +1181,115 @@ __global__ void band_graph_kernel(const long long *every, int P, int64_t cols,
     }
 }
 
+// weighted mode: the same two tables with 128-bit deliveries:
+// out[0 / 1][c] = low / high word of the flow delivered into column c of the band above,
+// out[2 / 3][c] = the same for the band below, out[4 / 5][c] = links as in band_tables_kernel
+__global__ void band_tables_w_kernel(const i128 *agg, const int32_t *root, int64_t rows, int64_t cols,
+                                     int tiles_x, int tiles_y, int64_t vfirst, long long *out)
+{
+    const int last_ty = tiles_y - 1;
+    const int last_h = (int)(rows - (int64_t)last_ty * T);
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const i128 up = agg[vfirst + c], dn = agg[vfirst + cols + c];
+        out[c] = (long long)up.lo;
+        out[cols + c] = up.hi;
+        out[2 * cols + c] = (long long)dn.lo;
+        out[3 * cols + c] = dn.hi;
+        const int64_t tx = c / T, lx = c % T;
+        const int64_t top = tx * SLOTS + lx;
+        const int64_t bot = ((int64_t)last_ty * tiles_x + tx) * SLOTS + (last_h == 1 ? lx : T + lx);
+        const long long rt = (long long)root[top] - vfirst, rb = (long long)root[bot] - vfirst;
+        out[4 * cols + c] = rt >= 0 ? rt : -1;
+        out[5 * cols + c] = rb >= 0 ? rb : -1;
+    }
+}
+
+__global__ void band_graph_w_kernel(const long long *every, int P, int64_t cols, i128 *base,
+                                    int32_t *next)
+{
+    const int64_t n = (int64_t)P * 2 * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / (2 * cols));
+        const int s = (int)((i / cols) & 1);
+        const int64_t c = i % cols;
+        i128 v(0);
+        if (s == 0 && b > 0) { // sent down by the band above
+            const long long *e = every + ((int64_t)(b - 1) * 6 + 2) * cols;
+            v = i128((unsigned long long)e[c], e[cols + c]);
+        }
+        if (s == 1 && b < P - 1) { // sent up by the band below
+            const long long *e = every + ((int64_t)(b + 1) * 6 + 0) * cols;
+            v = i128((unsigned long long)e[c], e[cols + c]);
+        }
+        base[i] = v;
+        const long long L = every[((int64_t)b * 6 + 4 + s) * cols + c];
+        int32_t nx = -1;
+        if (L >= 0) {
+            const long long side = L / cols, c2 = L - side * cols;
+            nx = side == 0 ? (int32_t)(((int64_t)(b - 1) * 2 + 1) * cols + c2)
+                           : (int32_t)(((int64_t)(b + 1) * 2 + 0) * cols + c2);
+        }
+        next[i] = nx;
+    }
+}
+
+// boundary-graph slot of column c of the band's first (top) / last row
+__device__ __forceinline__ int64_t edge_slot(bool top, int64_t c, int64_t rows, int tiles_x, int tiles_y)
+{
+    const int64_t tx = c / T, lx = c % T;
+    if (top)
+        return tx * SLOTS + lx;
+    const int last_ty = tiles_y - 1;
+    const int last_h = (int)(rows - (int64_t)last_ty * T);
+    return ((int64_t)last_ty * tiles_x + tx) * SLOTS + (last_h == 1 ? lx : T + lx);
+}
+
+// count modes: tag the slots of the band's first / last row (where flow from a neighbour
+// band can come in); the mark rides through the resolve in the upper bits of the sums
+__global__ void mark_edges_kernel(unsigned long long *base0, int64_t rows, int64_t cols, int tiles_x,
+                                  int tiles_y, int top, int bot)
+{
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        // a band of one tile row and height 1 has top == bottom slots; atomics keep both marks
+        if (top)
+            atomicAdd(base0 + edge_slot(true, c, rows, tiles_x, tiles_y), 1ull << MARK_SHIFT);
+        if (bot)
+            atomicAdd(base0 + edge_slot(false, c, rows, tiles_x, tiles_y), 1ull << MARK_SHIFT);
+    }
+}
+
+// add the flows the neighbour bands deliver into the band's first / last row to the
+// boundary graph (before a second full resolve)
+template <typename V>
+__global__ void add_imports_kernel(V *base0, const V *imp_top, const V *imp_bot, int64_t rows,
+                                   int64_t cols, int tiles_x, int tiles_y)
+{
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        if (imp_top)
+            atomic_add_v(base0 + edge_slot(true, c, rows, tiles_x, tiles_y), imp_top[c]);
+        if (imp_bot)
+            atomic_add_v(base0 + edge_slot(false, c, rows, tiles_x, tiles_y), imp_bot[c]);
+    }
+}
+
 struct Workspace {
     uint16_t *lacc;
     int64_t lacc_ld;
+    long long *lacc64;
+    int64_t lacc64_ld;
+    int32_t *tile_e;
     void *base0, *aggA, *aggB, *arr0, *arr1;
     int32_t *next0, *ptrA, *ptrB, *rootA, *rootB, *list, *idmap, *rootC, *list2;
     void *base2;
     int *nlist2;
     int *flags, *nlist;
+    unsigned *gmax_bits;
     int64_t nslots;
+    int vsize; // bytes per boundary-graph value: 8 (u64 counts) or 16 (i128 weighted sums)
 };
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
@@ -957,23 +1299,31 @@ int64_t nslots_of(int64_t rows, int64_t cols)
     return (int64_t)ht::cdiv(rows, T) * ht::cdiv(cols, T) * SLOTS + 2 * cols;
 }
 
-size_t workspace_bytes(int64_t rows, int64_t cols)
+// count modes: u64 values, u16 tile-local counts; weighted: i128 values, int64
+// tile-local sums + one int32 per tile
+size_t workspace_bytes(int64_t rows, int64_t cols, int mode)
 {
     const int64_t n = nslots_of(rows, cols);
-    const int64_t lacc_ld = (cols + 7) / 8 * 8;
-    return 6 * align_up(n * 8) + 9 * align_up(n * 4) + align_up(128 * sizeof(int)) +
-           align_up((size_t)rows * lacc_ld * 2) + 256;
+    const size_t vs = mode == W_F32 ? 16 : 8;
+    size_t local;
+    if (mode == W_F32)
+        local = align_up((size_t)rows * ((cols + 1) / 2 * 2) * 8) +
+                align_up((size_t)ht::cdiv(rows, T) * ht::cdiv(cols, T) * 4);
+    else
+        local = align_up((size_t)rows * ((cols + 7) / 8 * 8) * 2);
+    return 6 * align_up(n * vs) + 9 * align_up(n * 4) + align_up(128 * sizeof(int)) + local + 256;
 }
 
-int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
+int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, int mode, Workspace &w)
 {
-    if (!ws || ws_bytes < workspace_bytes(rows, cols))
+    if (!ws || ws_bytes < workspace_bytes(rows, cols, mode))
         return HT_ERR_WORKSPACE;
     const int64_t n = nslots_of(rows, cols);
+    const size_t vs = mode == W_F32 ? 16 : 8;
     uint8_t *b = (uint8_t *)(((uintptr_t)ws + 255) / 256 * 256);
-    w.base0 = b; b += align_up(n * 8);
-    w.aggA = b; b += align_up(n * 8);
-    w.aggB = b; b += align_up(n * 8);
+    w.base0 = b; b += align_up(n * vs);
+    w.aggA = b; b += align_up(n * vs);
+    w.aggB = b; b += align_up(n * vs);
     w.next0 = (int32_t *)b; b += align_up(n * 4);
     w.ptrA = (int32_t *)b; b += align_up(n * 4);
     w.ptrB = (int32_t *)b; b += align_up(n * 4);
@@ -983,15 +1333,26 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, Workspace &w)
     w.idmap = (int32_t *)b; b += align_up(n * 4);
     w.rootC = (int32_t *)b; b += align_up(n * 4);
     w.list2 = (int32_t *)b; b += align_up(n * 4);
-    w.base2 = b; b += align_up(n * 8);
-    w.arr0 = b; b += align_up(n * 8);
-    w.arr1 = b; b += align_up(n * 8);
+    w.base2 = b; b += align_up(n * vs);
+    w.arr0 = b; b += align_up(n * vs);
+    w.arr1 = b; b += align_up(n * vs);
     w.flags = (int *)b; b += align_up(128 * sizeof(int));
     w.nlist = w.flags + 64;
     w.nlist2 = w.flags + 65;
-    w.lacc = (uint16_t *)b;
-    w.lacc_ld = (cols + 7) / 8 * 8;
+    w.gmax_bits = (unsigned *)(w.flags + 100);
+    w.lacc = nullptr; w.lacc_ld = 0; w.lacc64 = nullptr; w.lacc64_ld = 0; w.tile_e = nullptr;
+    if (mode == W_F32) {
+        w.lacc64 = (long long *)b;
+        w.lacc64_ld = (cols + 1) / 2 * 2;
+        b += align_up((size_t)rows * w.lacc64_ld * 8);
+        w.tile_e = (int32_t *)b;
+    }
+    else {
+        w.lacc = (uint16_t *)b;
+        w.lacc_ld = (cols + 7) / 8 * 8;
+    }
     w.nslots = n;
+    w.vsize = (int)vs;
     return 0;
 }
 
@@ -1004,11 +1365,16 @@ int make_packed_map(CUtensorMap &map, const uint8_t *packed, int64_t packed_ld, 
 }
 
 template <bool FINAL>
-int launch_f64(const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
+int launch_w(const CUtensorMap &map, const AccArgs &p, cudaStream_t st)
 {
-    auto kern = acc_f64_kernel<FINAL>;
-    HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMD_TOTAL));
-    kern<<<p.tiles_x * p.tiles_y, THREADS, SMD_TOTAL, st>>>(map, p);
+    if (FINAL) {
+        HT_CUDA_TRY(cudaFuncSetAttribute(acc_final_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMX_TOTAL));
+        acc_final_w_kernel<<<p.tiles_x * p.tiles_y, THREADS, SMX_TOTAL, st>>>(map, p);
+    }
+    else {
+        HT_CUDA_TRY(cudaFuncSetAttribute(acc_local_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMW_TOTAL));
+        acc_local_w_kernel<<<p.tiles_x * p.tiles_y, THREADS, SMW_TOTAL, st>>>(map, p);
+    }
     HT_LAUNCH_CHECK();
     return 0;
 }
@@ -1037,7 +1403,7 @@ int dispatch_tile(int mode, const CUtensorMap &map, const AccArgs &p, cudaStream
     switch (mode) {
     case W_ONE: return launch_cnt<W_ONE, FINAL>(map, p, st);
     case W_TAINT: return launch_cnt<W_TAINT, FINAL>(map, p, st);
-    case W_F32: return launch_f64<FINAL>(map, p, st);
+    case W_F32: return launch_w<FINAL>(map, p, st);
     }
     return HT_ERR_ARG;
 }
@@ -1089,6 +1455,7 @@ int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t tota
     p.acc = nullptr; p.acc_ld = 0; p.dir_out = nullptr; p.dir_ld = 0;
     p.lacc = nullptr; p.lacc_ld = 0; p.packed = nullptr; p.packed_ld = 0;
     p.list = nullptr; p.nlist = nullptr;
+    p.lacc64 = nullptr; p.lacc64_ld = 0; p.tile_e = nullptr; p.gmax_bits = nullptr;
     return 0;
 }
 
@@ -1098,7 +1465,49 @@ extern "C" size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols)
 {
     if (rows <= 0 || cols <= 0)
         return 256;
-    return workspace_bytes(rows, cols);
+    return workspace_bytes(rows, cols, W_ONE);
+}
+
+extern "C" size_t ht_acc_workspace_bytes_mode(int64_t rows, int64_t cols, int mode)
+{
+    if (rows <= 0 || cols <= 0 || mode < 0 || mode > 2)
+        return 256;
+    return workspace_bytes(rows, cols, mode);
+}
+
+// Weighted mode: bits of the largest finite |weight| (nodata / NaN / inf skipped) of the
+// caller's rows, as a float in an unsigned (non-negative floats order like their bits, so
+// row bands combine their values with an integer MAX all-reduce).
+extern "C" int ht_acc_weight_max(const float *w, int64_t w_ld, int64_t rows, int64_t cols,
+                                 int has_wnd, float wnd, unsigned *max_bits, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!max_bits || rows < 0 || cols < 0 || (rows > 0 && cols > 0 && (!w || w_ld < cols)))
+        return HT_ERR_ARG;
+    HT_CUDA_TRY(cudaMemsetAsync(max_bits, 0, sizeof(unsigned), st));
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    const int64_t n = rows * cols;
+    const int grid = (int)min((int64_t)ht::kSMs * 8, (n + 255) / 256);
+    weight_max_kernel<<<grid, 256, 0, st>>>(w, w_ld, rows, cols, has_wnd, wnd, max_bits);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
+}
+
+// Weighted mode: hand the (all-reduced) maximum to the workspace; it fixes the global
+// fixed-point unit of stages A, B and C.
+extern "C" int ht_acc_set_weight_max(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
+                                     const unsigned *max_bits, void *stream)
+{
+    if (rows <= 0 || cols <= 0 || !max_bits)
+        return HT_ERR_ARG;
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, W_F32, wk);
+    if (rc)
+        return rc;
+    HT_CUDA_TRY(cudaMemcpyAsync(wk.gmax_bits, max_bits, sizeof(unsigned), cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream));
+    return HT_OK;
 }
 
 // Stage A.  After it, the workspace holds the band's boundary graph.
@@ -1117,16 +1526,17 @@ extern "C" int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t ro
     if (!packed || packed_ld < cols || (mode == W_F32 && (!w || w_ld < cols)) || mode < 0 || mode > 2)
         return HT_ERR_ARG;
     Workspace wk;
-    if ((rc = carve(ws, ws_bytes, rows, cols, wk)))
+    if ((rc = carve(ws, ws_bytes, rows, cols, mode, wk)))
         return rc;
     CUtensorMap map;
     if ((rc = make_packed_map(map, packed, packed_ld, rows, cols, p.halo_top, p.halo_bot)))
         return rc;
-    HT_CUDA_TRY(cudaMemsetAsync(wk.base0, 0, wk.nslots * 8, st));
+    HT_CUDA_TRY(cudaMemsetAsync(wk.base0, 0, wk.nslots * wk.vsize, st));
     HT_CUDA_TRY(cudaMemsetAsync(wk.next0, 0xFF, wk.nslots * 4, st));
     p.base = wk.base0; p.next = wk.next0;
     p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
     p.lacc = wk.lacc; p.lacc_ld = wk.lacc_ld;
+    p.lacc64 = wk.lacc64; p.lacc64_ld = wk.lacc64_ld; p.tile_e = wk.tile_e; p.gmax_bits = wk.gmax_bits;
     p.packed = packed; p.packed_ld = packed_ld;
     p.list = wk.list; p.nlist = wk.nlist;
     HT_CUDA_TRY(cudaMemsetAsync(wk.nlist, 0, sizeof(int), st));
@@ -1148,26 +1558,75 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
 {
     if (rows == 0 || cols == 0)
         return HT_OK;
+    if (mode < 0 || mode > 2)
+        return HT_ERR_ARG;
     Workspace wk;
-    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    int rc = carve(ws, ws_bytes, rows, cols, mode, wk);
     if (rc)
         return rc;
     // rootB is the slot-ordered output ("last node of each slot's path")
     int32_t *rA = want_roots ? wk.rootA : nullptr, *rC = want_roots ? wk.rootC : nullptr;
     int32_t *rOut = want_roots ? wk.rootB : nullptr;
-    HT_CUDA_TRY(cudaMemsetAsync(wk.aggB, 0, wk.nslots * 8, (cudaStream_t)stream));
+    HT_CUDA_TRY(cudaMemsetAsync(wk.aggB, 0, wk.nslots * wk.vsize, (cudaStream_t)stream));
     if (mode == W_F32)
-        return launch_resolve<double>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist, wk.idmap,
-                                      wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1, rA, rC, wk.aggB,
-                                      rOut, wk.flags, rounds_dev, (cudaStream_t)stream);
+        return launch_resolve<i128>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist, wk.idmap,
+                                    wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1, rA, rC, wk.aggB,
+                                    rOut, wk.flags, rounds_dev, (cudaStream_t)stream);
     return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist,
                                               wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
                                               rA, rC, wk.aggB, rOut, wk.flags, rounds_dev,
                                               (cudaStream_t)stream);
 }
 
+// Row-band sharding, count modes, after ht_acc_local: tag the slots of the band's first
+// (halo_top) / last (halo_bot) row so that ht_acc_resolve leaves a mark on every node
+// downstream of them (see ht_acc_resolve_delta).
+extern "C" int ht_acc_mark_edges(int64_t rows, int64_t cols, int mode, int halo_top, int halo_bot,
+                                 void *ws, size_t ws_bytes, void *stream)
+{
+    if (rows <= 0 || cols <= 0 || mode == W_F32 || mode < 0 || mode > 2)
+        return HT_ERR_ARG;
+    if (!halo_top && !halo_bot)
+        return HT_OK;
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, mode, wk);
+    if (rc)
+        return rc;
+    mark_edges_kernel<<<ht::cdiv(cols, 256), 256, 0, (cudaStream_t)stream>>>(
+        (unsigned long long *)wk.base0, rows, cols, ht::cdiv(cols, T), ht::cdiv(rows, T),
+        halo_top ? 1 : 0, halo_bot ? 1 : 0);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
+}
+
+// Row-band sharding: add the flows the neighbour bands deliver into the band's first /
+// last row (imp_top / imp_bot: cols values of the mode's type -- u64 counts or 128-bit
+// weighted sums -- or NULL) to the boundary graph; a second ht_acc_resolve follows.
+extern "C" int ht_acc_add_imports(int64_t rows, int64_t cols, int mode, const void *imp_top,
+                                  const void *imp_bot, void *ws, size_t ws_bytes, void *stream)
+{
+    if (rows <= 0 || cols <= 0 || mode < 0 || mode > 2)
+        return HT_ERR_ARG;
+    if (!imp_top && !imp_bot)
+        return HT_OK;
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, mode, wk);
+    if (rc)
+        return rc;
+    const int grid = ht::cdiv(cols, 256), tiles_x = ht::cdiv(cols, T), tiles_y = ht::cdiv(rows, T);
+    if (mode == W_F32)
+        add_imports_kernel<i128><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            (i128 *)wk.base0, (const i128 *)imp_top, (const i128 *)imp_bot, rows, cols, tiles_x, tiles_y);
+    else
+        add_imports_kernel<unsigned long long><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            (unsigned long long *)wk.base0, (const unsigned long long *)imp_top,
+            (const unsigned long long *)imp_bot, rows, cols, tiles_x, tiles_y);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
+}
+
 // Row-band sharding, count modes.  ht_acc_resolve must have run on a boundary graph
-// whose band-edge slots carried a mark (1 << 48 added to base0); `imp_top` /
+// whose band-edge slots carried a mark (1 << 40 added to base0; ht_acc_mark_edges); `imp_top` /
 // `imp_bot` (cols values each, or NULL) are the flows the neighbour bands deliver
 // into the cells of the band's first / last row.  Adds their effect to the resolved
 // inflow of every node downstream and clears the marks -- a resolve over the
@@ -1180,10 +1639,10 @@ extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
     cudaStream_t st = (cudaStream_t)stream;
     if (rows == 0 || cols == 0)
         return HT_OK;
-    if (mode == W_F32)
+    if (mode == W_F32 || mode < 0 || mode > 2)
         return HT_ERR_ARG; // marks need integer sums
     Workspace wk;
-    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    int rc = carve(ws, ws_bytes, rows, cols, mode, wk);
     if (rc)
         return rc;
     HT_CUDA_TRY(cudaMemsetAsync(wk.nlist2, 0, sizeof(int), st));
@@ -1198,37 +1657,46 @@ extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
                                               st, 1);
 }
 
-extern "C" int ht_band_tables(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
-                              long long *out4, void *stream)
+extern "C" int ht_band_tables(int64_t rows, int64_t cols, int mode, void *ws, size_t ws_bytes,
+                              long long *out, void *stream)
 {
-    if (rows <= 0 || cols <= 0 || !out4)
+    if (rows <= 0 || cols <= 0 || !out || mode < 0 || mode > 2)
         return HT_ERR_ARG;
     Workspace wk;
-    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    int rc = carve(ws, ws_bytes, rows, cols, mode, wk);
     if (rc)
         return rc;
-    band_tables_kernel<<<ht::cdiv(cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const unsigned long long *)wk.aggB, wk.rootB, rows, cols, ht::cdiv(cols, T),
-        ht::cdiv(rows, T), wk.nslots - 2 * cols, out4);
+    if (mode == W_F32)
+        band_tables_w_kernel<<<ht::cdiv(cols, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const i128 *)wk.aggB, wk.rootB, rows, cols, ht::cdiv(cols, T), ht::cdiv(rows, T),
+            wk.nslots - 2 * cols, out);
+    else
+        band_tables_kernel<<<ht::cdiv(cols, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const unsigned long long *)wk.aggB, wk.rootB, rows, cols, ht::cdiv(cols, T),
+            ht::cdiv(rows, T), wk.nslots - 2 * cols, out);
     HT_LAUNCH_CHECK();
     return HT_OK;
 }
 
-extern "C" int ht_band_graph(const long long *every, int bands, int64_t cols,
-                             unsigned long long *base, int32_t *next, void *stream)
+extern "C" int ht_band_graph(const long long *every, int bands, int64_t cols, int mode, void *base,
+                             int32_t *next, void *stream)
 {
-    if (!every || !base || !next || bands <= 0 || cols <= 0 ||
+    if (!every || !base || !next || bands <= 0 || cols <= 0 || mode < 0 || mode > 2 ||
         (int64_t)bands * 2 * cols >= INT32_MAX)
         return HT_ERR_ARG;
-    band_graph_kernel<<<ht::cdiv((int64_t)bands * 2 * cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        every, bands, cols, base, next);
+    const int grid = ht::cdiv((int64_t)bands * 2 * cols, 256);
+    if (mode == W_F32)
+        band_graph_w_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(every, bands, cols, (i128 *)base, next);
+    else
+        band_graph_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(every, bands, cols,
+                                                                  (unsigned long long *)base, next);
     HT_LAUNCH_CHECK();
     return HT_OK;
 }
 
-// Byte offsets (from the workspace pointer) of the boundary-graph arrays, for the
-// row-band host code: layout[0..8] = base0, aggA, aggB (= resolved inflow), next0,
-// ptrA, ptrB, rootA, rootB (= last node of each path), flags; layout[9] = number
+// Byte offsets (from the workspace pointer) of the boundary-graph arrays of a COUNT-mode
+// workspace, for tests and tools: layout[0..8] = base0, aggA, aggB (= resolved inflow),
+// next0, ptrA, ptrB, rootA, rootB (= last node of each path), flags; layout[9] = number
 // of slots, layout[10] = first virtual slot (cells of the band above, then of the
 // band below, `cols` each).
 extern "C" int ht_acc_workspace_layout(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
@@ -1237,7 +1705,7 @@ extern "C" int ht_acc_workspace_layout(int64_t rows, int64_t cols, void *ws, siz
     if (!layout11 || rows <= 0 || cols <= 0)
         return HT_ERR_ARG;
     Workspace wk;
-    int rc = carve(ws, ws_bytes, rows, cols, wk);
+    int rc = carve(ws, ws_bytes, rows, cols, W_ONE, wk);
     if (rc)
         return rc;
     const uint8_t *b = (const uint8_t *)ws;
@@ -1251,28 +1719,34 @@ extern "C" int ht_acc_workspace_layout(int64_t rows, int64_t cols, void *ws, siz
 
 // Generic forest resolve (subtree sums): agg_out[v] = base[v] + sum of base[u] over
 // all u whose path along next[] passes through v.  Resolves the band-level boundary
-// graph of a row-band sharded raster.  is_f64: values are doubles, else u64.
-extern "C" int ht_forest_resolve(const void *base, const int32_t *next, int64_t n, int is_f64,
+// graph of a row-band sharded raster.  vtype: 0 = u64, 1 = fp64, 2 = 128-bit integers
+// (16 B per value).  tmp_bytes >= (3 * value size + 8) * n + 4096.
+extern "C" int ht_forest_resolve(const void *base, const int32_t *next, int64_t n, int vtype,
                                  void *agg_out, void *tmp, size_t tmp_bytes, void *stream)
 {
     if (n == 0)
         return HT_OK;
-    if (!base || !next || !agg_out || !tmp || n < 0)
+    if (!base || !next || !agg_out || !tmp || n < 0 || vtype < 0 || vtype > 2)
         return HT_ERR_ARG;
-    const size_t need = 3 * align_up(n * 8) + 2 * align_up(n * 4) + 512 + 256;
+    const size_t vs = vtype == 2 ? 16 : 8;
+    const size_t need = 3 * align_up(n * vs) + 2 * align_up(n * 4) + 512 + 256;
     if (tmp_bytes < need)
         return HT_ERR_WORKSPACE;
     uint8_t *b = (uint8_t *)(((uintptr_t)tmp + 255) / 256 * 256);
-    void *a = b; b += align_up(n * 8);
-    void *arr0 = b; b += align_up(n * 8);
-    void *arr1 = b; b += align_up(n * 8);
+    void *a = b; b += align_up(n * vs);
+    void *arr0 = b; b += align_up(n * vs);
+    void *arr1 = b; b += align_up(n * vs);
     int32_t *ptrA = (int32_t *)b; b += align_up(n * 4);
     int32_t *ptrB = (int32_t *)b; b += align_up(n * 4);
     int *flags = (int *)b;
-    if (is_f64)
+    if (vtype == 1)
         return launch_resolve<double>(base, next, n, nullptr, nullptr, nullptr, ptrA, ptrB, a, arr0,
                                       arr1, nullptr, nullptr, agg_out, nullptr, flags, nullptr,
                                       (cudaStream_t)stream);
+    if (vtype == 2)
+        return launch_resolve<i128>(base, next, n, nullptr, nullptr, nullptr, ptrA, ptrB, a, arr0,
+                                    arr1, nullptr, nullptr, agg_out, nullptr, flags, nullptr,
+                                    (cudaStream_t)stream);
     return launch_resolve<unsigned long long>(base, next, n, nullptr, nullptr, nullptr, ptrA, ptrB, a,
                                               arr0, arr1, nullptr, nullptr, agg_out, nullptr, flags,
                                               nullptr, (cudaStream_t)stream);
@@ -1293,26 +1767,24 @@ extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t ro
     int rc = fill_args(p, rows, cols, row0, total_rows, halo_top, halo_bot);
     if (rc)
         return rc;
-    if (!packed || packed_ld < cols || (mode == W_F32 && (!w || w_ld < cols)) || mode < 0 ||
-        mode > 2 || (acc && acc_ld < cols) || (dir_out && dir_ld < cols))
+    if (!packed || packed_ld < cols || mode < 0 || mode > 2 || (acc && acc_ld < cols) ||
+        (dir_out && dir_ld < cols))
         return HT_ERR_ARG;
     // count modes store 2 doubles / 4 direction bytes at a time
     if (mode != W_F32 && ((acc && (((uintptr_t)acc & 15) || (acc_ld & 1))) ||
                           (dir_out && (((uintptr_t)dir_out & 3) || (dir_ld & 3)))))
         return HT_ERR_ALIGN;
     Workspace wk;
-    if ((rc = carve(ws, ws_bytes, rows, cols, wk)))
+    if ((rc = carve(ws, ws_bytes, rows, cols, mode, wk)))
         return rc;
     CUtensorMap map;
-    if (mode == W_F32)
-        rc = make_packed_map(map, packed, packed_ld, rows, cols, p.halo_top, p.halo_bot);
-    else
-        rc = ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1,
-                             packed - (int64_t)p.halo_top * packed_ld,
-                             rows + p.halo_top + p.halo_bot, cols, packed_ld, T, T, false);
+    rc = ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1,
+                         packed - (int64_t)p.halo_top * packed_ld,
+                         rows + p.halo_top + p.halo_bot, cols, packed_ld, T, T, false);
     if (rc)
         return rc;
     p.lacc = wk.lacc; p.lacc_ld = wk.lacc_ld;
+    p.lacc64 = wk.lacc64; p.lacc64_ld = wk.lacc64_ld; p.tile_e = wk.tile_e; p.gmax_bits = wk.gmax_bits;
     p.packed = packed; p.packed_ld = packed_ld;
     p.inflow = wk.aggB;
     p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
@@ -1326,8 +1798,16 @@ extern "C" int ht_acc_f64(const uint8_t *packed, int64_t packed_ld, int64_t rows
                           double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld,
                           void *ws, size_t ws_bytes, void *stream)
 {
-    int rc = ht_acc_local(packed, packed_ld, rows, cols, 0, rows, 0, 0, mode, w, w_ld, has_wnd,
-                          wnd, ws, ws_bytes, stream);
+    int rc;
+    if (mode == W_F32 && rows > 0 && cols > 0) {
+        Workspace wk;
+        if ((rc = carve(ws, ws_bytes, rows, cols, mode, wk)))
+            return rc;
+        if ((rc = ht_acc_weight_max(w, w_ld, rows, cols, has_wnd, wnd, wk.gmax_bits, stream)))
+            return rc;
+    }
+    rc = ht_acc_local(packed, packed_ld, rows, cols, 0, rows, 0, 0, mode, w, w_ld, has_wnd,
+                      wnd, ws, ws_bytes, stream);
     if (rc)
         return rc;
     if ((rc = ht_acc_resolve(rows, cols, mode, 0, ws, ws_bytes, nullptr, stream)))

@@ -7,13 +7,17 @@
 
 namespace {
 
+// rows [-halo_top, rows + halo_bot) of the allocation are packed (halo rows = the edge rows of
+// the neighbour bands, which the accumulation stages read as their ring); `dir` points at
+// owned row 0, global row = row0 + local row
 __global__ void pack_i8_kernel(const int8_t *dir, int64_t ld, int64_t rows, int64_t cols,
+                               int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
                                uint8_t *packed, int64_t packed_ld)
 {
-    const int64_t n = rows * cols;
+    const int64_t n = (rows + halo_top + halo_bot) * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cols, c = i - r * cols;
+        const int64_t r = i / cols - halo_top, c = i - (r + halo_top) * cols;
         const int d = dir[r * ld + c];
         uint8_t b;
         if (d == -128)
@@ -23,8 +27,10 @@ __global__ void pack_i8_kernel(const int8_t *dir, int64_t ld, int64_t rows, int6
             // pass flow on" (the accumulation kernels then never re-check a target)
             const int64_t rr = r + (int)((0x1A900u >> (2 * d)) & 3u) - 1;
             const int64_t cc = c + (int)((0x29018u >> (2 * d)) & 3u) - 1;
-            const bool gone = rr < 0 || rr >= rows || cc < 0 || cc >= cols ||
-                              dir[rr * ld + cc] == -128;
+            bool gone = row0 + rr < 0 || row0 + rr >= total_rows || cc < 0 || cc >= cols;
+            // a halo row's receiver may lie beyond the rows this band holds: nobody asks
+            if (!gone && rr >= -halo_top && rr < rows + halo_bot)
+                gone = dir[rr * ld + cc] == -128;
             b = (uint8_t)d | (gone ? HT_DIR_EDGE : 0);
         }
         else if (d <= -1 && d >= -8)
@@ -75,7 +81,26 @@ extern "C" int ht_dir_pack_i8(const int8_t *dir, int64_t ld, int64_t rows, int64
         return HT_ERR_ARG;
     if (rows == 0 || cols == 0)
         return HT_OK;
-    pack_i8_kernel<<<ht::kSMs * 8, 256, 0, (cudaStream_t)stream>>>(dir, ld, rows, cols, packed, packed_ld);
+    pack_i8_kernel<<<ht::kSMs * 8, 256, 0, (cudaStream_t)stream>>>(dir, ld, rows, cols, 0, rows, 0, 0,
+                                                                  packed, packed_ld);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
+}
+
+// Row-band form: `dir` / `packed` point at the band's first OWNED row; with halo_top /
+// halo_bot the edge row of the neighbour band sits directly above / below in both
+// allocations (the direction row arrives by exchange, the packed row is written here).
+extern "C" int ht_dir_pack_band_i8(const int8_t *dir, int64_t ld, int64_t rows, int64_t cols,
+                                   int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                                   uint8_t *packed, int64_t packed_ld, void *stream)
+{
+    if (!dir || !packed || rows < 0 || cols < 0 || ld < cols || packed_ld < cols || row0 < 0 ||
+        total_rows < row0 + rows || (!halo_top && row0 != 0) || (!halo_bot && row0 + rows != total_rows))
+        return HT_ERR_ARG;
+    if (rows == 0 || cols == 0)
+        return HT_OK;
+    pack_i8_kernel<<<ht::kSMs * 8, 256, 0, (cudaStream_t)stream>>>(
+        dir, ld, rows, cols, row0, total_rows, halo_top ? 1 : 0, halo_bot ? 1 : 0, packed, packed_ld);
     HT_LAUNCH_CHECK();
     return HT_OK;
 }

@@ -65,15 +65,26 @@ def upload(a: ArrayLike, dtype: torch.dtype, align_elems: int, device,
         if t.dtype != dtype:
             t = t.to(dtype)
         if not t.is_pinned():
-            # pageable host memory: stage through a cached pinned buffer
+            # pageable host memory: stage through a cached pinned buffer.  The buffer is
+            # reused by the next upload of the same dtype, so wait until the DMA of the
+            # previous one has drained before the CPU overwrites it.
+            key = ("upload", t.dtype)
+            pending = _STAGE_BUSY.pop(key, None)
+            if pending is not None:
+                pending.synchronize()
             stage = _pinned(t.shape, t.dtype, "upload")
             stage.copy_(t)
-            t = stage
-        view.copy_(t, non_blocking=True)
+            view.copy_(stage, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            _STAGE_BUSY[key] = done
+        else:
+            view.copy_(t, non_blocking=True)
     return buf, ld
 
 
 _PINNED = {}
+_STAGE_BUSY = {}  # (tag, dtype) -> CUDA event recorded after the last H2D copy out of the stage
 
 
 def _pinned(shape, dtype, tag: str) -> torch.Tensor:

@@ -52,13 +52,18 @@ SIGNATURES = {
     "ht_d8_validate_conditioned_f32": [_p, _i64, _i64, _i64, _int, _f32, _i64, _i64, _int,
                                        _int, _p, _p],
     "ht_dir_pack_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],
+    "ht_dir_pack_band_i8": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _p, _i64, _p],
     "ht_dir_unpack_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],
     "ht_acc_local": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _i64, _int,
                      _f32, _p, C.c_size_t, _p],
     "ht_acc_resolve": [_i64, _i64, _int, _int, _p, C.c_size_t, _p, _p],
     "ht_acc_resolve_delta": [_i64, _i64, _int, _p, _p, _p, C.c_size_t, _p],
-    "ht_band_tables": [_i64, _i64, _p, C.c_size_t, _p, _p],
-    "ht_band_graph": [_p, _int, _i64, _p, _p, _p],
+    "ht_acc_mark_edges": [_i64, _i64, _int, _int, _int, _p, C.c_size_t, _p],
+    "ht_acc_add_imports": [_i64, _i64, _int, _p, _p, _p, C.c_size_t, _p],
+    "ht_acc_weight_max": [_p, _i64, _i64, _i64, _int, _f32, _p, _p],
+    "ht_acc_set_weight_max": [_i64, _i64, _p, C.c_size_t, _p, _p],
+    "ht_band_tables": [_i64, _i64, _int, _p, C.c_size_t, _p, _p],
+    "ht_band_graph": [_p, _int, _i64, _int, _p, _p, _p],
     "ht_acc_final": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _i64, _int,
                      _f32, _p, _i64, _p, _i64, _p, C.c_size_t, _p],
     "ht_acc_f64": [_p, _i64, _i64, _i64, _int, _p, _i64, _int, _f32, _p, _i64, _p, _i64,
@@ -81,6 +86,8 @@ def _declare():
 _declare()
 lib.ht_acc_workspace_bytes.argtypes = [_i64, _i64]
 lib.ht_acc_workspace_bytes.restype = C.c_size_t
+lib.ht_acc_workspace_bytes_mode.argtypes = [_i64, _i64, _int]
+lib.ht_acc_workspace_bytes_mode.restype = C.c_size_t
 lib.ht_window_filter_runs_workspace_bytes.argtypes = [_i64, _i64, _int]
 lib.ht_window_filter_runs_workspace_bytes.restype = C.c_size_t
 

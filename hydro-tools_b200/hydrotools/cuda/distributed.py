@@ -4,8 +4,8 @@
 NVLink, and the boundary graph is resolved iteratively until no flow changes").
 
 One process per GPU (torchrun); ``torch.distributed`` is the plumbing:
-  * DEM halo rows (2 per shared side for D8, 1 for the terrain stencils) travel
-    with point-to-point send/recv between band neighbours;
+  * DEM halo rows (2 per shared side for D8, 1 for the terrain stencils): every band
+    contributes its first / last rows to one all-gather and picks its neighbours' rows;
   * accumulation: every band resolves its own tile boundary graph first, then
     publishes two small tables per shared side -- the flow it delivers into each
     cell of the neighbour's edge row, and, for each of its own edge-row cells,
@@ -100,6 +100,8 @@ class BandEngine:
         if self.world > 1:
             dist.all_reduce(c, group=self.group)
         c = c.cpu()
+        if int(c[2]):
+            raise ValueError(f"{int(c[2])} cells have |elevation| >= 2**24 mm (16 777 m); not supported")
         return int(c[0]), int(c[1])
 
     # ----------------------------------------------------------------- comm
@@ -136,12 +138,37 @@ class BandEngine:
             band.apply_sign()
             self.launches += band.take_launches()
 
+    def load_direction(self, direction):
+        """A STORED direction raster (this rank's rows; int8 GRASS codes, -128 NULL) instead
+        of a DEM: FlowAccumulation(direction), /root/reference/src/hydrotools/watershed.py:
+        329-339, sharded.  Edge rows travel to the band neighbours (one all-gather of two int8
+        rows per band), then the band is packed with r.flowaccumulation's semantics -- a code
+        whose receiver is NULL or outside the raster ends the path, every other cell passes
+        its flow on -- exactly as hydrotools.cuda.flow_accumulation_arrays does unsharded."""
+        band, P = self.band, self.world
+        band.set_direction(direction)
+        if P > 1:
+            send = band.dir_edge_rows()  # [2, cols] int8: first, last row
+            every = torch.empty((P * 2, self.cols), dtype=send.dtype, device=send.device)
+            dist.all_gather_into_tensor(every, send, group=self.group)
+            every = every.view(P, 2, self.cols)
+            band.set_dir_halo(every[self.rank - 1, 1] if self.rank > 0 else None,
+                              every[self.rank + 1, 0] if self.rank < P - 1 else None)
+        band.pack_direction()
+        self.launches += band.take_launches()
+
     def flow_accumulation(self, weight, weight_nodata: Optional[float] = None):
         """Weighted accumulation (FlowAccumulation.calculate(..., "sum"),
         /root/reference/src/hydrotools/watershed.py:357-382) over the direction grid the
         last flow_direction_accumulation() left on the device: ``weight`` = this rank's rows
         of the weight raster.  Returns this rank's rows of the fp64 sums."""
         band = self.band
+        if weight is None:  # cell counts ("modals", watershed.py:341-355)
+            band.stash_accumulation()
+            self.accumulate(band.N.MODE_COUNT, want_dir=False)
+            out = band.acc[:, :self.cols].clone()
+            band.unstash_accumulation()
+            return out
         band.set_weight(weight, weight_nodata)
         band.stash_accumulation()
         self.accumulate(band.N.MODE_WEIGHTED)
@@ -149,29 +176,37 @@ class BandEngine:
         band.unstash_accumulation()
         return out
 
-    def accumulate(self, mode: int = 0):
+    def accumulate(self, mode: int = 0, want_dir: bool = True):
         band = self.band
+        if mode == 2 and hasattr(band, "weight_max"):
+            # weighted sums are exact fixed point; the unit follows from the largest
+            # |weight| of the WHOLE raster: one 4-byte MAX all-reduce
+            m = band.weight_max()
+            if self.world > 1:
+                dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+            band.set_weight_max(m)
         band.local(mode)
         if self.world == 1:
             band.resolve(False)
-            band.final(mode)
+            band.final(mode, want_dir) if want_dir is False else band.final(mode)
             self.launches += band.take_launches()
             return
-        # count modes: band-edge slots carry a mark through the first resolve, so that the
-        # second one only has to visit the nodes downstream of the band edge
-        delta = hasattr(band, "resolve_delta") and band.supports_delta(mode)
-        if delta:
-            band.mark_edges(mode)
-        band.resolve(True)
         P = self.world
-        if delta and hasattr(band, "band_tables4"):
-            # counts on the device: both tables from one kernel, one collective, and the
-            # band-level forest from one kernel
-            both = band.band_tables4()  # [4, cols] int64
-            every = torch.empty((P * 4, self.cols), dtype=torch.int64, device=both.device)
-            dist.all_gather_into_tensor(every, both, group=self.group)
-            base, nxt = band.band_graph(every, P)
+        if hasattr(band, "publish_tables"):
+            # product backend: tables, band-level forest and the hand-back of the imported
+            # flow are kernels behind the C-ABI; torch only moves the all-gather
+            delta = band.supports_delta(mode)
+            if delta:
+                # count modes: band-edge slots carry a mark through the first resolve, so
+                # that the second one only visits the nodes downstream of the band edge
+                band.mark_edges(mode)
+            band.resolve(True)
+            mine = band.publish_tables(mode)  # [4 or 6, cols] int64
+            every = torch.empty((P * mine.shape[0], self.cols), dtype=torch.int64, device=mine.device)
+            dist.all_gather_into_tensor(every, mine, group=self.group)
+            band.import_flows(every, P, self.rank, mode, delta)
         else:
+            band.resolve(True)
             delivered, link = band.band_tables(mode)
             # (P*k, cols): concatenation along dim 0 is the layout every backend accepts
             if delivered.dtype == torch.int64:
@@ -186,13 +221,10 @@ class BandEngine:
                 dist.all_gather_into_tensor(all_d, delivered.contiguous(), group=self.group)
                 dist.all_gather_into_tensor(all_l, link.contiguous(), group=self.group)
             base, nxt = build_band_graph(all_d.reshape(P, 2, self.cols), all_l.reshape(P, 2, self.cols))
-        inflow = band.forest_resolve(base, nxt, mode).view(P, 2, self.cols)
-        if delta:
-            band.resolve_delta(inflow[self.rank, 0], inflow[self.rank, 1], mode)
-        else:
+            inflow = band.forest_resolve(base, nxt, mode).view(P, 2, self.cols)
             band.add_inflow(inflow[self.rank, 0], inflow[self.rank, 1], mode)
             band.resolve(False)
-        band.final(mode)
+        band.final(mode, want_dir) if want_dir is False else band.final(mode)
         self.launches += band.take_launches()
 
     def terrain(self, scale: float = 1.0, percent: bool = False):
@@ -256,6 +288,7 @@ class CudaBand:
         self.dir, self.dld = D.empty_padded(rows, cols, torch.int8, self.dev, 16)
         self.ws = torch.empty(int(N.lib.ht_acc_workspace_bytes(rows, cols)), dtype=torch.uint8,
                               device=self.dev)
+        self._ws_w = None  # weighted mode: 128-bit sums and 8 B/cell of tile-local sums
         import ctypes
         lay = (ctypes.c_int64 * 11)()
         N.check(N.lib.ht_acc_workspace_layout(rows, cols, self.ws.data_ptr(), self.ws.numel(), lay),
@@ -266,8 +299,17 @@ class CudaBand:
         self.weight, self.wld, self.wnd = None, 0, None
         self._launches = 0
         self._tmp = None
-        self._mark = None
         self._acc2 = None
+        self._mode = 0
+
+    def _wsm(self, mode):
+        """Workspace of `mode` (the weighted one is allocated on first use)."""
+        if mode != self.N.MODE_WEIGHTED:
+            return self.ws
+        if self._ws_w is None:
+            n = int(self.N.lib.ht_acc_workspace_bytes_mode(self.rows, self.cols, mode))
+            self._ws_w = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        return self._ws_w
 
     # ---- pointers
     def _dem0(self):
@@ -311,6 +353,34 @@ class CudaBand:
     def dem_view(self):
         return self.dem[2:2 + self.rows, :self.cols]
 
+    # ---- a stored direction raster instead of a DEM
+    def set_direction(self, d):
+        if getattr(self, "dir_in", None) is None:
+            self.dir_in, self.dil = self.D.empty_padded(self.rows, self.cols, torch.int8, self.dev,
+                                                        16, 1, 1)
+        a = self.D.as_2d(d)
+        view = self.dir_in[1:1 + self.rows, :self.cols]
+        if isinstance(a, torch.Tensor):
+            view.copy_(a.to(torch.int8), non_blocking=True)
+        else:
+            import numpy as np
+            view.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.int8)), non_blocking=False)
+
+    def dir_edge_rows(self):
+        return torch.stack([self.dir_in[1, :self.cols], self.dir_in[self.rows, :self.cols]])
+
+    def set_dir_halo(self, above, below):
+        if above is not None:
+            self.dir_in[0, :self.cols].copy_(above)
+        if below is not None:
+            self.dir_in[self.rows + 1, :self.cols].copy_(below)
+
+    def pack_direction(self):
+        self.N.call("ht_dir_pack_band_i8", self.dir_in.data_ptr() + self.dil, self.dil, self.rows,
+                    self.cols, self.row0, self.total_rows, int(self.htop > 0), int(self.hbot > 0),
+                    self._packed0(), self.pld, self.D.stream_ptr())
+        self._launches += 1
+
     def edge_rows(self, top, depth):
         r0 = 2 if top else 2 + self.rows - depth
         return self.dem[r0:r0 + depth, :self.cols].contiguous()
@@ -342,36 +412,54 @@ class CudaBand:
             return self.weight.data_ptr(), self.wld, has, nd
         return None, 0, 0, 0.0
 
+    def weight_max(self):
+        """Bits of the largest finite |weight| of this band (int32 tensor of one element)."""
+        w, wld, has, nd = self._wargs(self.N.MODE_WEIGHTED)
+        m = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.N.call("ht_acc_weight_max", w, wld, self.rows, self.cols, has, nd, m.data_ptr(),
+                    self.D.stream_ptr())
+        self._launches += 1
+        return m
+
+    def set_weight_max(self, m):
+        ws = self._wsm(self.N.MODE_WEIGHTED)
+        self.N.call("ht_acc_set_weight_max", self.rows, self.cols, ws.data_ptr(), ws.numel(),
+                    m.data_ptr(), self.D.stream_ptr())
+
     def local(self, mode=0):
         w, wld, has, nd = self._wargs(mode)
+        ws = self._wsm(mode)
         self.N.call("ht_acc_local", self._packed0(), self.pld, self.rows, self.cols, self.row0,
                     self.total_rows, int(self.htop > 0), int(self.hbot > 0), mode, w, wld, has, nd,
-                    self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
+                    ws.data_ptr(), ws.numel(), self.D.stream_ptr())
         self._launches += 1
         self._mode = mode
 
     def resolve(self, want_roots):
+        ws = self._wsm(self._mode)
         self.N.call("ht_acc_resolve", self.rows, self.cols, self._mode, int(want_roots),
-                    self.ws.data_ptr(), self.ws.numel(), None, self.D.stream_ptr())
+                    ws.data_ptr(), ws.numel(), None, self.D.stream_ptr())
         self._launches += 1
 
     def resolve_rounds(self) -> int:
         """Pointer-doubling rounds stage B needs on the current boundary graph."""
         r = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.N.call("ht_acc_resolve", self.rows, self.cols, self._mode, 0, self.ws.data_ptr(),
-                    self.ws.numel(), r.data_ptr(), self.D.stream_ptr())
+        ws = self._wsm(self._mode)
+        self.N.call("ht_acc_resolve", self.rows, self.cols, self._mode, 0, ws.data_ptr(),
+                    ws.numel(), r.data_ptr(), self.D.stream_ptr())
         return int(r.item())
 
     def final(self, mode=0, want_dir=True):
         w, wld, has, nd = self._wargs(mode)
+        ws = self._wsm(mode)
         self.N.call("ht_acc_final", self._packed0(), self.pld, self.rows, self.cols, self.row0,
                     self.total_rows, int(self.htop > 0), int(self.hbot > 0), mode, w, wld, has, nd,
                     self.acc.data_ptr(), self.ald,
                     self.dir.data_ptr() if (want_dir and mode == 0) else None, self.dld,
-                    self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
+                    ws.data_ptr(), ws.numel(), self.D.stream_ptr())
         self._launches += 1
 
-    MARK = 1 << 48  # band-edge mark in the u64 sums of the boundary graph (csrc/ht_acc.cu)
+    MARK = 1 << 40  # band-edge mark in the u64 sums of the boundary graph (csrc/ht_acc.cu)
 
     def supports_delta(self, mode):
         return mode != self.N.MODE_WEIGHTED
@@ -380,13 +468,10 @@ class CudaBand:
         """After stage A: tag the slots of the band's first / last row (where flow from a
         neighbour band can come in) so that the resolve leaves a mark on every node
         downstream of them."""
-        base0 = self._ws_view(0, torch.int64)
-        if self._mark is None:
-            self._mark = torch.full((self.cols,), self.MARK, dtype=torch.int64, device=self.dev)
-        if self.htop:
-            base0.index_add_(0, self.idx_top, self._mark)
-        if self.hbot:
-            base0.index_add_(0, self.idx_bot, self._mark)
+        ws = self._wsm(mode)
+        self.N.call("ht_acc_mark_edges", self.rows, self.cols, mode, int(self.htop > 0),
+                    int(self.hbot > 0), ws.data_ptr(), ws.numel(), self.D.stream_ptr())
+        self._launches += 1
 
     def resolve_delta(self, top, bot, mode=0):
         """Second resolve of a sharded run, over the marked nodes only."""
@@ -398,53 +483,84 @@ class CudaBand:
                     self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
         self._launches += 2
 
-    def band_tables4(self):
-        """Count modes: [delivered up, delivered down, link top, link bottom] x cols (int64),
-        one kernel."""
-        out = torch.empty((4, self.cols), dtype=torch.int64, device=self.dev)
-        self.N.call("ht_band_tables", self.rows, self.cols, self.ws.data_ptr(), self.ws.numel(),
+    def publish_tables(self, mode=0):
+        """The tables this band publishes after resolve(want_roots=True), one kernel:
+        count modes [delivered up, delivered down, link top, link bottom] x cols; weighted
+        mode the two deliveries as 128-bit integers (low, high words): 6 x cols (int64)."""
+        k = 6 if mode == self.N.MODE_WEIGHTED else 4
+        out = torch.empty((k, self.cols), dtype=torch.int64, device=self.dev)
+        ws = self._wsm(mode)
+        self.N.call("ht_band_tables", self.rows, self.cols, mode, ws.data_ptr(), ws.numel(),
                     out.data_ptr(), self.D.stream_ptr())
         self._launches += 1
         return out
 
-    def band_graph(self, every, bands):
-        """Band-level forest (base u64 as int64, next int32) from the all-gathered tables."""
+    def band_tables4(self):
+        return self.publish_tables(0)
+
+    def band_graph(self, every, bands, mode=0):
+        """Band-level forest (base: u64 as int64, or [n, 2] int64 = 128-bit values in
+        weighted mode; next int32) from the all-gathered tables."""
         n = bands * 2 * self.cols
-        base = torch.empty(n, dtype=torch.int64, device=self.dev)
+        wide = mode == self.N.MODE_WEIGHTED
+        base = torch.empty((n, 2) if wide else (n,), dtype=torch.int64, device=self.dev)
         nxt = torch.empty(n, dtype=torch.int32, device=self.dev)
-        self.N.call("ht_band_graph", every.data_ptr(), bands, self.cols, base.data_ptr(),
+        self.N.call("ht_band_graph", every.data_ptr(), bands, self.cols, mode, base.data_ptr(),
                     nxt.data_ptr(), self.D.stream_ptr())
         self._launches += 1
         return base, nxt
 
+    def import_flows(self, every, bands, rank, mode, delta):
+        """Band-level forest from the all-gathered tables, its resolve, and the hand-back of
+        the flow this band imports: a resolve over the marked nodes (count modes) or the
+        imports added to the boundary graph and a second full resolve (weighted)."""
+        base, nxt = self.band_graph(every, bands, mode)
+        inflow = self.forest_resolve(base, nxt, mode)
+        wide = mode == self.N.MODE_WEIGHTED
+        inflow = inflow.view(bands, 2, self.cols, 2) if wide else inflow.view(bands, 2, self.cols)
+        top, bot = inflow[rank, 0], inflow[rank, 1]  # contiguous slices
+        if delta:
+            self.resolve_delta(top, bot, mode)
+            return
+        ws = self._wsm(mode)
+        self.N.call("ht_acc_add_imports", self.rows, self.cols, mode,
+                    top.data_ptr() if self.htop else None, bot.data_ptr() if self.hbot else None,
+                    ws.data_ptr(), ws.numel(), self.D.stream_ptr())
+        self._launches += 1
+        self.resolve(False)
+
     def band_tables(self, mode=0):
-        """(delivered [2, cols], link [2, cols]) after resolve(want_roots=True)."""
-        vd = self._vdtype(mode)
-        inflow = self._ws_view(2, vd)       # aggB
+        """Count modes, torch formulation of publish_tables (tests compare the two):
+        (delivered [2, cols], link [2, cols]) after resolve(want_roots=True)."""
+        if mode == self.N.MODE_WEIGHTED:
+            raise ValueError("weighted tables are 128-bit: use publish_tables")
+        inflow = self._ws_view(2, torch.int64)       # aggB
         root = self._ws_view(7, torch.int32)  # rootB
         delivered = inflow[self.vfirst:self.vfirst + 2 * self.cols].view(2, self.cols).clone()
-        if vd == torch.int64:
-            delivered &= self.MARK - 1
+        delivered &= self.MARK - 1
         link = torch.stack([root[self.idx_top], root[self.idx_bot]]).to(torch.int64) - self.vfirst
         link = torch.where(link >= 0, link, torch.full_like(link, -1)).to(torch.int32)
         return delivered, link
 
     def forest_resolve(self, base, nxt, mode=0):
-        n = base.numel()
+        n = nxt.numel()
         out = torch.empty_like(base)
-        need = 32 * n + 8192
+        wide = mode == self.N.MODE_WEIGHTED
+        need = (56 if wide else 32) * n + 8192
         if self._tmp is None or self._tmp.numel() < need:
             self._tmp = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        self.N.call("ht_forest_resolve", base.data_ptr(), nxt.data_ptr(), n,
-                    int(mode == self.N.MODE_WEIGHTED), out.data_ptr(), self._tmp.data_ptr(),
-                    self._tmp.numel(), self.D.stream_ptr())
+        self.N.call("ht_forest_resolve", base.data_ptr(), nxt.data_ptr(), n, 2 if wide else 0,
+                    out.data_ptr(), self._tmp.data_ptr(), self._tmp.numel(), self.D.stream_ptr())
         self._launches += 1
         return out
 
     def add_inflow(self, top, bot, mode=0):
-        base0 = self._ws_view(0, self._vdtype(mode))
-        base0.index_add_(0, self.idx_top, top)
-        base0.index_add_(0, self.idx_bot, bot)
+        """Count modes: imports added to the boundary graph before a second full resolve."""
+        self.N.call("ht_acc_add_imports", self.rows, self.cols, mode,
+                    top.contiguous().data_ptr() if self.htop else None,
+                    bot.contiguous().data_ptr() if self.hbot else None,
+                    self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
+        self._launches += 1
 
     def terrain(self, scale=1.0, percent=False):
         outs = [self.D.empty_padded(self.rows, self.cols, torch.float32, self.dev, 4) for _ in range(3)]

@@ -26,8 +26,9 @@ from . import _io
 DIR_NODATA = -128  # hydrotools.utils.infer_nodata("int8")
 
 
-def _workspace(rows: int, cols: int, dev) -> torch.Tensor:
-    return torch.empty(int(N.lib.ht_acc_workspace_bytes(rows, cols)), dtype=torch.uint8, device=dev)
+def _workspace(rows: int, cols: int, dev, mode: int = 0) -> torch.Tensor:
+    return torch.empty(int(N.lib.ht_acc_workspace_bytes_mode(rows, cols, mode)), dtype=torch.uint8,
+                       device=dev)
 
 
 def validate_conditioned(dem: D.ArrayLike, nodata: Optional[float] = None) -> Tuple[int, int]:
@@ -70,7 +71,7 @@ def accumulate(packed: torch.Tensor, pld: int, rows: int, cols: int, mode: int,
     acc, ald = D.empty_padded(rows, cols, torch.float64, dev, 2)
     dout, dld = (D.empty_padded(rows, cols, torch.int8, dev, 16) if want_dir else (None, 0))
     if ws is None:
-        ws = _workspace(rows, cols, dev)
+        ws = _workspace(rows, cols, dev, mode)
     has, nd = D.nodata_args(weight_nodata)
     N.call("ht_acc_f64", packed.data_ptr(), pld, rows, cols, mode,
            weight.data_ptr() if weight is not None else None, wld, has, nd,

@@ -92,6 +92,12 @@ int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,
  * flow on), which is what r.flowaccumulation does with it. */
 int ht_dir_pack_i8(const int8_t *dir, int64_t ld, int64_t rows, int64_t cols,
                    uint8_t *packed, int64_t packed_ld, void *stream);
+/* row-band form: `dir` / `packed` point at the band's first owned row; with halo_top /
+ * halo_bot (0 / 1) the edge row of the neighbour band sits directly above / below in both
+ * allocations (the direction row arrived by exchange; its packed byte is written too) */
+int ht_dir_pack_band_i8(const int8_t *dir, int64_t ld, int64_t rows, int64_t cols,
+                        int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                        uint8_t *packed, int64_t packed_ld, void *stream);
 int ht_dir_unpack_i8(const uint8_t *packed, int64_t packed_ld, int64_t rows,
                      int64_t cols, int8_t *dir, int64_t ld, void *stream);
 
@@ -99,7 +105,7 @@ int ht_dir_unpack_i8(const uint8_t *packed, int64_t packed_ld, int64_t rows,
  * replaces  GRASS r.watershed accumulation=fa [-a]   (watershed.py:64-75)
  *      and  GRASS r.flowaccumulation [weight=]      (watershed.py:341-382)
  * mode: 0 = cell count, 1 = count of tainted cells upstream (sign step),
- *       2 = fp32 weights summed in fp64.
+ *       2 = fp32 weights, summed exactly in fixed point, reported as fp64.
  * Stage A (ht_acc_local) builds the tile boundary graph in the workspace,
  * stage B (ht_acc_resolve) resolves it by pointer doubling until no pointer
  * changes, stage C (ht_acc_final) writes acc (fp64; NaN where NULL) and, if
@@ -107,18 +113,29 @@ int ht_dir_unpack_i8(const uint8_t *packed, int64_t packed_ld, int64_t rows,
  * Count modes: acc 16-B aligned with acc_ld % 2 == 0, dir_out 4-B aligned with
  * dir_ld % 4 == 0 (HT_ERR_ALIGN otherwise).
  * ht_acc_f64 = A + B + C for an unsharded raster. */
-size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols);
-/* byte offsets of the boundary-graph arrays inside the workspace (row-band host
- * code reads the band tables from them): layout11[0..8] = base0, aggA,
- * aggB (resolved inflow), next0, ptrA, ptrB, rootA, rootB (last node of each
- * slot's path), flags; [9] = slots; [10] = first virtual slot (cells of the band
- * above, then of the band below, `cols` each). */
+size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols); /* count modes */
+/* mode 2 carries 128-bit sums and 8 B/cell of tile-local sums: a larger workspace */
+size_t ht_acc_workspace_bytes_mode(int64_t rows, int64_t cols, int mode);
+/* weighted mode works in exact fixed point (bit-reproducible, no fp64 atomics); the
+ * unit follows from the raster's largest finite |weight|.  ht_acc_weight_max writes its
+ * bits (a non-negative float stored in an unsigned, so that row bands combine theirs with
+ * an integer MAX all-reduce), ht_acc_set_weight_max hands the result to the workspace
+ * before ht_acc_local(mode 2).  ht_acc_f64 does both itself. */
+int ht_acc_weight_max(const float *w, int64_t w_ld, int64_t rows, int64_t cols, int has_wnd,
+                      float wnd, unsigned *max_bits, void *stream);
+int ht_acc_set_weight_max(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
+                          const unsigned *max_bits, void *stream);
+/* byte offsets of the boundary-graph arrays inside a COUNT-mode workspace (tests and
+ * tools): layout11[0..8] = base0, aggA, aggB (resolved inflow), next0, ptrA, ptrB,
+ * rootA, rootB (last node of each slot's path), flags; [9] = slots; [10] = first
+ * virtual slot (cells of the band above, then of the band below, `cols` each). */
 int ht_acc_workspace_layout(int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
                             int64_t *layout11_host);
 /* subtree sums over a forest given by next[] (< 0 = root); the band-level
  * boundary graph of a row-band sharded raster is resolved with it.
- * tmp_bytes >= 32*n + 4096. */
-int ht_forest_resolve(const void *base, const int32_t *next, int64_t n, int is_f64,
+ * vtype: 0 = u64, 1 = fp64, 2 = 128-bit integers {u64 lo, i64 hi} (weighted mode).
+ * tmp_bytes >= (3 * value size + 8) * n + 4096. */
+int ht_forest_resolve(const void *base, const int32_t *next, int64_t n, int vtype,
                       void *agg_out, void *tmp, size_t tmp_bytes, void *stream);
 int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
                  int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
@@ -126,25 +143,35 @@ int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t
                  void *ws, size_t ws_bytes, void *stream);
 int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roots, void *ws,
                    size_t ws_bytes, int *rounds_dev, void *stream);
-/* row-band sharding, count modes: after ht_acc_resolve on a graph whose band-edge
- * slots carried a mark (1 << 48 added to their base0 entry), add the effect of the
- * flows the neighbour bands deliver into the band's first / last row (imp_top /
+/* row-band sharding, count modes, after ht_acc_local: tag the boundary-graph slots of the
+ * band's first (halo_top) / last (halo_bot) row with a mark (1 << 40 added to their base0
+ * entry) that rides through ht_acc_resolve to every node downstream */
+int ht_acc_mark_edges(int64_t rows, int64_t cols, int mode, int halo_top, int halo_bot,
+                      void *ws, size_t ws_bytes, void *stream);
+/* row-band sharding, count modes: after ht_acc_resolve on a marked graph, add the effect of
+ * the flows the neighbour bands deliver into the band's first / last row (imp_top /
  * imp_bot: cols values each, or NULL) and clear the marks -- a resolve over the
  * nodes downstream of the band edge instead of a second full one */
 int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
                          const unsigned long long *imp_top,
                          const unsigned long long *imp_bot, void *ws, size_t ws_bytes,
                          void *stream);
-/* row-band sharding, count modes, after ht_acc_resolve(want_roots = 1): the tables a
- * band publishes, out4[4][cols] (int64): [0] / [1] flow delivered into column c of
- * the edge row of the band above / below, [2] / [3] for the band's own first / last
- * row cell c the foreign cell its path finally reaches (side * cols + column, side
- * 0 = band above) or -1 */
-int ht_band_tables(int64_t rows, int64_t cols, void *ws, size_t ws_bytes, long long *out4,
-                   void *stream);
-/* the band-level forest from the all-gathered tables every[bands][4][cols]:
- * base[bands][2][cols], next[bands][2][cols] for ht_forest_resolve */
-int ht_band_graph(const long long *every, int bands, int64_t cols, unsigned long long *base,
+/* row-band sharding, any mode: add the imported flows (cols values of the mode's type, u64
+ * or 128-bit, or NULL) to the boundary graph; a second full ht_acc_resolve follows */
+int ht_acc_add_imports(int64_t rows, int64_t cols, int mode, const void *imp_top,
+                       const void *imp_bot, void *ws, size_t ws_bytes, void *stream);
+/* row-band sharding, after ht_acc_resolve(want_roots = 1): the tables a band publishes.
+ * count modes: out[4][cols] (int64): [0] / [1] flow delivered into column c of the edge
+ * row of the band above / below, [2] / [3] for the band's own first / last row cell c the
+ * foreign cell its path finally reaches (side * cols + column, side 0 = band above) or -1.
+ * mode 2: out[6][cols]: [0],[1] low / high word of the 128-bit delivery to the band above,
+ * [2],[3] to the band below, [4],[5] the links. */
+int ht_band_tables(int64_t rows, int64_t cols, int mode, void *ws, size_t ws_bytes,
+                   long long *out, void *stream);
+/* the band-level forest from the all-gathered tables every[bands][4 or 6][cols]:
+ * base[bands][2][cols] (u64, or 128-bit in mode 2), next[bands][2][cols] for
+ * ht_forest_resolve */
+int ht_band_graph(const long long *every, int bands, int64_t cols, int mode, void *base,
                   int32_t *next, void *stream);
 int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
                  int64_t row0, int64_t total_rows, int halo_top, int halo_bot,

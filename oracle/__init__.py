@@ -119,10 +119,12 @@ def condition_by_rank(dem, nodata=None, ewres=1.0, nsres=1.0):
     return out
 
 
-def gdaldem(dem, nodata=None, ewres=1.0, nsres=1.0, scale=1.0, percent=False):
+def gdaldem(dem, nodata=None, ewres=1.0, nsres=1.0, scale=1.0, percent=False, threads=1):
     """gdaldem slope/aspect/TRI -compute_edges: (slope, aspect, tri) float32,
-    nodata -9999."""
+    nodata -9999.  ``threads`` > 1: rows in parallel (pthreads), for the all-core CPU
+    baseline; gdaldem itself is single-threaded."""
     dem = _dem(dem)
+    lib().ora_set_threads(int(threads))
     has, nd = _nd(nodata)
     s, a, t = (np.empty_like(dem) for _ in range(3))
     lib().ora_gdaldem(dem, dem.shape[0], dem.shape[1], has, nd, ewres, nsres,

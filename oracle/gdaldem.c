@@ -32,11 +32,15 @@
  */
 #include <math.h>
 #include <float.h>
+#include <pthread.h>
 #include <stdint.h>
 
 #include "oracle.h"
 
 #define DST_NODATA (-9999.0f)
+
+static int ora_threads = 1;
+void ora_set_threads(int n) { ora_threads = n > 0 ? n : 1; }
 
 static int are_real_equal(float a, float b)
 {
@@ -107,9 +111,59 @@ static float tri_riley(const float *w)
     return (float)sqrt(s);
 }
 
+typedef struct {
+    const float *dem;
+    int64_t rows, cols, row_lo, row_hi;
+    int has_nodata;
+    float nodata;
+    double ewres, nsres, scale;
+    int slope_percent;
+    float *slope, *aspect, *tri;
+} job_t;
+
+static int gdaldem_rows(const float *dem, int64_t rows, int64_t cols, int has_nodata,
+                        float nodata, double ewres, double nsres, double scale,
+                        int slope_percent, float *slope, float *aspect, float *tri,
+                        int64_t row_lo, int64_t row_hi);
+
+static void *job_main(void *arg)
+{
+    job_t *j = (job_t *)arg;
+    gdaldem_rows(j->dem, j->rows, j->cols, j->has_nodata, j->nodata, j->ewres, j->nsres,
+                 j->scale, j->slope_percent, j->slope, j->aspect, j->tri, j->row_lo, j->row_hi);
+    return NULL;
+}
+
+/* Rows are independent.  gdaldem itself is single-threaded (ora_set_threads(1), the
+ * default); bench.py's all-core CPU baseline asks for more (pthreads, one block of rows
+ * per thread). */
 int ora_gdaldem(const float *dem, int64_t rows, int64_t cols, int has_nodata,
                 float nodata, double ewres, double nsres, double scale,
                 int slope_percent, float *slope, float *aspect, float *tri)
+{
+    int nt = ora_threads;
+    if (nt > 256)
+        nt = 256;
+    if (nt <= 1 || rows < 2 * nt)
+        return gdaldem_rows(dem, rows, cols, has_nodata, nodata, ewres, nsres, scale,
+                            slope_percent, slope, aspect, tri, 0, rows);
+    pthread_t th[256];
+    job_t jobs[256];
+    for (int t = 0; t < nt; t++) {
+        job_t j = {dem, rows, cols, rows * t / nt, rows * (t + 1) / nt, has_nodata, nodata,
+                   ewres, nsres, scale, slope_percent, slope, aspect, tri};
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < nt; t++)
+        pthread_join(th[t], NULL);
+    return 0;
+}
+
+static int gdaldem_rows(const float *dem, int64_t rows, int64_t cols, int has_nodata,
+                        float nodata, double ewres, double nsres, double scale,
+                        int slope_percent, float *slope, float *aspect, float *tri,
+                        int64_t row_lo, int64_t row_hi)
 {
     nd_t nd = {has_nodata, nodata, has_nodata && isnan(nodata)};
     if (rows < 2 || cols < 2) {
@@ -124,7 +178,7 @@ int ora_gdaldem(const float *dem, int64_t rows, int64_t cols, int has_nodata,
         return 0;
     }
 #define L(i, j) dem[(int64_t)(i) * cols + (j)]
-    for (int64_t i = 0; i < rows; i++) {
+    for (int64_t i = row_lo; i < row_hi; i++) {
         for (int64_t j = 0; j < cols; j++) {
             float w[9];
             if (i == 0 || i == rows - 1) {

@@ -33,6 +33,8 @@ int ora_gdaldem(const float *dem, int64_t rows, int64_t cols, int has_nodata,
                 float nodata, double ewres, double nsres, double scale,
                 int slope_percent, float *slope, float *aspect, float *tri);
 
+void ora_set_threads(int n); /* threads of ora_gdaldem (default 1) */
+
 /* flowacc.c */
 int ora_flowacc_count(const int8_t *dir, int64_t rows, int64_t cols,
                       double *acc);

@@ -32,34 +32,53 @@ def run_bands(dem, cuts, nodata, csx, csy, mode=0, weight=None, delta=False):
             bands[b].set_halo_rows(top=True, rows=bands[b - 1].edge_rows(top=False, depth=2))
         if b < P - 1:
             bands[b].set_halo_rows(top=False, rows=bands[b + 1].edge_rows(top=True, depth=2))
+    return accumulate_bands(bands, mode, delta)
+
+
+def accumulate_bands(bands, mode=0, delta=False, direction=True):
+    """The exchange of BandEngine.accumulate with the collective replaced by a
+    concatenation (every band lives on this one GPU)."""
+    from hydrotools.cuda import distributed as HD, _native as N
+    P, cols = len(bands), bands[0].cols
+    weighted = mode == N.MODE_WEIGHTED
+    if weighted:  # the MAX all-reduce of BandEngine.accumulate
+        m = torch.stack([band.weight_max() for band in bands]).max().reshape(1)
+        for band in bands:
+            band.set_weight_max(m)
     tabs = []
     for band in bands:
-        band.direction()
+        if direction:
+            band.direction()
         band.local(mode)
         if delta:
             band.mark_edges(mode)
         band.resolve(True)
-        tabs.append(band.band_tables(mode))
-    all_d = torch.stack([t[0] for t in tabs])
-    all_l = torch.stack([t[1] for t in tabs])
-    base, nxt = HD.build_band_graph(all_d, all_l)
-    if delta:
-        # the fused kernels BandEngine uses in count modes give the same tables / forest
-        every = torch.cat([band.band_tables4() for band in bands])
-        for b in range(P):
-            assert torch.equal(every[4 * b:4 * b + 2], tabs[b][0])
-            assert torch.equal(every[4 * b + 2:4 * b + 4], tabs[b][1].to(torch.int64))
-        base2, nxt2 = bands[0].band_graph(every, P)
-        assert torch.equal(base2, base) and torch.equal(nxt2, nxt)
-        base, nxt = base2, nxt2
-    inflow = bands[0].forest_resolve(base, nxt, mode).view(P, 2, cols)
-    outs = []
-    for b, band in enumerate(bands):
-        if delta:  # resolve over the nodes downstream of the band edge only
-            band.resolve_delta(inflow[b, 0], inflow[b, 1], mode)
-        else:      # second full resolve
+        if not weighted:
+            tabs.append(band.band_tables(mode))
+    if weighted or delta:
+        # the kernels BandEngine uses: tables, band-level forest, hand-back of the imports
+        every = torch.cat([band.publish_tables(mode) for band in bands])
+        if not weighted:  # ... agree with their torch formulation
+            all_d = torch.stack([t[0] for t in tabs])
+            all_l = torch.stack([t[1] for t in tabs])
+            base, nxt = HD.build_band_graph(all_d, all_l)
+            for b in range(P):
+                assert torch.equal(every[4 * b:4 * b + 2], tabs[b][0])
+                assert torch.equal(every[4 * b + 2:4 * b + 4], tabs[b][1].to(torch.int64))
+            base2, nxt2 = bands[0].band_graph(every, P)
+            assert torch.equal(base2, base) and torch.equal(nxt2, nxt)
+        for b, band in enumerate(bands):
+            band.import_flows(every, P, b, mode, delta)
+    else:
+        all_d = torch.stack([t[0] for t in tabs])
+        all_l = torch.stack([t[1] for t in tabs])
+        base, nxt = HD.build_band_graph(all_d, all_l)
+        inflow = bands[0].forest_resolve(base, nxt, mode).view(P, 2, cols)
+        for b, band in enumerate(bands):  # second full resolve
             band.add_inflow(inflow[b, 0], inflow[b, 1], mode)
             band.resolve(False)
+    outs = []
+    for band in bands:
         band.final(mode)
         fd, fa = band.results()
         outs.append((fd.cpu().numpy(), fa.cpu().numpy()))
@@ -122,3 +141,40 @@ def test_bands_weighted(hc):
     exp = oracle.flowacc(d, w)
     m = ~np.isnan(exp)
     np.testing.assert_allclose(acc[m], exp[m], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("cuts", [[0, 100, 333, 500], [0, 64, 65, 300, 500], [0, 500]])
+def test_bands_stored_direction(hc, golden, cuts):
+    """Row a3 sharded: accumulation over a STORED direction raster in row bands equals the
+    unsharded function and plain oracle.flowacc (r.flowaccumulation semantics: every cell
+    passes its flow on unless the receiver is NULL / outside)."""
+    from hydrotools.cuda import distributed as HD, _native as N
+    dem = oracle.synth_dem(3, 500, 400, with_nulls=True)
+    w = oracle.synth_weight(3, 500, 400)
+    fd, _ = oracle.rwatershed(dem, ND, 10.0, 10.0)
+    total, cols = fd.shape
+    P = len(cuts) - 1
+    for mode, weight in ((N.MODE_WEIGHTED, w), (N.MODE_COUNT, None)):
+        bands = []
+        for b in range(P):
+            lo, hi = cuts[b], cuts[b + 1]
+            band = HD.CudaBand(hi - lo, cols, lo, total, 10.0, 10.0, None,
+                               has_above=b > 0, has_below=b < P - 1)
+            band.set_direction(fd[lo:hi])
+            if weight is not None:
+                band.set_weight(weight[lo:hi])
+            bands.append(band)
+        edges = [band.dir_edge_rows() for band in bands]  # BandEngine.load_direction's all-gather
+        for b, band in enumerate(bands):
+            band.set_dir_halo(edges[b - 1][1] if b > 0 else None, edges[b + 1][0] if b < P - 1 else None)
+            band.pack_direction()
+        _, acc = accumulate_bands(bands, mode, delta=(mode == N.MODE_COUNT and P > 1), direction=False)
+        exp = oracle.flowacc(fd, weight)
+        np.testing.assert_array_equal(np.isnan(acc), np.isnan(exp))
+        m = ~np.isnan(exp)
+        if weight is None:
+            np.testing.assert_array_equal(acc[m], exp[m])
+        else:
+            np.testing.assert_allclose(acc[m], exp[m], rtol=1e-12, atol=0)
+            whole = hc.flow_accumulation_arrays(fd, weight)
+            np.testing.assert_array_equal(acc, whole)  # exact fixed point: sharding changes nothing

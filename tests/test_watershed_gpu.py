@@ -127,10 +127,61 @@ def test_flowacc_synthetic_weighted(hc):
     exp = oracle.flowacc(fd, w)
     m = ~np.isnan(exp)
     np.testing.assert_allclose(got[m], exp[m], rtol=1e-5, atol=0)
-    # fixed gather order inside a tile, atomics only across tiles: run-to-run
-    # differences stay far below the contract
-    again = hc.flow_accumulation_arrays(fd, w)
-    np.testing.assert_allclose(again[m], got[m], rtol=1e-12)
+    # exact fixed point: integer adds commute, so the result is bit-reproducible
+    for _ in range(3):
+        again = hc.flow_accumulation_arrays(fd, w)
+        np.testing.assert_array_equal(again, got)
+    # ... and far tighter than the contract (quantisation at 2^-49 of a tile's largest weight)
+    np.testing.assert_allclose(got[m], exp[m], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("case", ["signed", "tiny_and_huge", "zeros", "nodata_nan_inf"])
+def test_flowacc_weight_ranges(hc, case):
+    """Fixed-point edge cases of the weighted mode: negative weights, 12 orders of
+    magnitude inside one raster, all-zero weights, NaN / inf / nodata weights."""
+    rng = np.random.default_rng(11)
+    dem = oracle.synth_dem(9, 400, 500, with_nulls=True)
+    fd, _ = oracle.rwatershed(dem, ND, 10.0, 10.0)
+    w = rng.uniform(0.5, 2.0, fd.shape).astype(np.float32)
+    wnd = None
+    if case == "signed":
+        w *= rng.choice([-1.0, 1.0], fd.shape).astype(np.float32)
+    elif case == "tiny_and_huge":
+        w[:, :250] *= np.float32(1e-6)
+        w[:, 250:] *= np.float32(1e6)
+    elif case == "zeros":
+        w[:] = 0
+    else:
+        wnd = -9999.0
+        w[rng.random(fd.shape) < 0.1] = wnd
+        w[rng.random(fd.shape) < 0.05] = np.nan
+        w[7, 9] = np.inf  # treated as no data (the oracle sums it: compare without it)
+    got = hc.flow_accumulation_arrays(fd, w, wnd)
+    we = w.copy()
+    we[~np.isfinite(we)] = np.nan
+    exp = oracle.flowacc(fd, we, wnd)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    m = ~np.isnan(exp)
+    if case == "signed":  # cancellation: compare against the magnitude that flowed in
+        mag = oracle.flowacc(fd, np.abs(we), wnd)
+        assert np.max(np.abs(got[m] - exp[m]) / np.maximum(mag[m], 1e-30)) < 1e-12
+    else:
+        np.testing.assert_allclose(got[m], exp[m], rtol=1e-9, atol=0)
+
+
+@pytest.mark.timeout(900)
+def test_config1_full_parity(hc):
+    """BASELINE.json configs[1] at its real size: the bench's own DEM (seed 20261019,
+    10 000 x 10 000) through the public array API, bit-exact against the oracle
+    (/root/reference/src/hydrotools/watershed.py:64-75).  The oracle needs ~4 GB and
+    about a minute on one core."""
+    n = 10000
+    dem = oracle.synth_dem(20261019, n, n)
+    fd, fa = hc.flow_direction_accumulation_arrays(dem, nodata=None, csx=10.0, csy=10.0)
+    efd, efa = oracle.rwatershed(dem, None, 10.0, 10.0)
+    del dem
+    np.testing.assert_array_equal(fd, efd)
+    np.testing.assert_array_equal(fa, efa)
 
 
 def test_misaligned_weight_raises(hc, golden):
