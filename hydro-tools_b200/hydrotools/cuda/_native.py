@@ -51,6 +51,8 @@ SIGNATURES = {
                   _p, _i64, _p],
     "ht_d8_validate_conditioned_f32": [_p, _i64, _i64, _i64, _int, _f32, _i64, _i64, _int,
                                        _int, _p, _p],
+    "ht_d8_general_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _p, _i64, _p, C.c_size_t,
+                          C.POINTER(C.c_longlong), _p],
     "ht_dir_pack_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],
     "ht_dir_pack_band_i8": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _p, _i64, _p],
     "ht_dir_unpack_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],
@@ -88,6 +90,8 @@ lib.ht_acc_workspace_bytes.argtypes = [_i64, _i64]
 lib.ht_acc_workspace_bytes.restype = C.c_size_t
 lib.ht_acc_workspace_bytes_mode.argtypes = [_i64, _i64, _int]
 lib.ht_acc_workspace_bytes_mode.restype = C.c_size_t
+lib.ht_d8_general_workspace_bytes.argtypes = [_i64, _i64]
+lib.ht_d8_general_workspace_bytes.restype = C.c_size_t
 lib.ht_window_filter_runs_workspace_bytes.argtypes = [_i64, _i64, _int]
 lib.ht_window_filter_runs_workspace_bytes.restype = C.c_size_t
 

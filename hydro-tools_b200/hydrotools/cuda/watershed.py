@@ -7,10 +7,12 @@ The reference shells out to GRASS ``r.watershed -s [-a]`` and the addon
 include/hydrotools_b200.h: ``ht_d8_f32`` (direction codes), ``ht_acc_*``
 (tile-local propagation, boundary-graph resolve, final pass).
 
-Scope (BASELINE.json north_star): single flow direction on hydrologically
-conditioned DEMs.  ``single=False`` (MFD) and ``beautify=True`` raise
-``NotImplementedError``; a DEM with pits or ties raises ``ValueError`` --
-there is no CPU fallback to GRASS.
+Scope (BASELINE.json north_star): single flow direction.  Hydrologically conditioned
+DEMs take the one-pass local-rule kernel; every other DEM (equal elevations, flats,
+depressions -- e.g. the reference's own test fixture) the general kernel
+(``ht_d8_general_f32``), which reproduces r.watershed's least-cost search exactly.
+``single=False`` (MFD) and ``beautify=True`` raise ``NotImplementedError``; there is no
+CPU fallback to GRASS.
 """
 import os
 from tempfile import TemporaryDirectory
@@ -62,6 +64,29 @@ def d8(dem: torch.Tensor, ld: int, rows: int, cols: int, nodata: Optional[float]
     return packed, pld
 
 
+def d8_general(dem: torch.Tensor, ld: int, rows: int, cols: int, nodata: Optional[float],
+               csx: float, csy: float) -> Tuple[torch.Tensor, int, dict]:
+    """Packed direction bytes of ANY DEM (ties, flats, depressions): r.watershed's
+    least-cost search reproduced exactly (csrc/ht_astar.cu).  Returns (packed, pitch, stats)."""
+    import ctypes
+    dev = dem.device
+    packed, pld = D.empty_padded(rows, cols, torch.uint8, dev, 16)
+    ws = torch.empty(int(N.lib.ht_d8_general_workspace_bytes(rows, cols)), dtype=torch.uint8, device=dev)
+    has, nd = D.nodata_args(nodata)
+    stats = (ctypes.c_longlong * 8)()
+    N.call("ht_d8_general_f32", dem.data_ptr(), rows, cols, ld, has, nd, float(abs(csx)),
+           float(abs(csy)), packed.data_ptr(), pld, ws.data_ptr(), ws.numel(), stats, D.stream_ptr())
+    names = ("rounds", "episodes", "largest_episode", "depression_cells", "fill_passes",
+             "generation_sweeps", "out_of_range", "errors")
+    info = dict(zip(names, (int(v) for v in stats)))
+    if info["out_of_range"]:
+        raise ValueError(f"{info['out_of_range']} cells have |elevation| >= 2**24 mm (16 777 m); not supported")
+    return packed, pld, info
+
+
+LAST_STATS = {}  # statistics of the last general-path run (diagnostics)
+
+
 def accumulate(packed: torch.Tensor, pld: int, rows: int, cols: int, mode: int,
                weight: Optional[torch.Tensor] = None, wld: int = 0,
                weight_nodata: Optional[float] = None, want_dir: bool = False,
@@ -84,7 +109,8 @@ def flow_direction_accumulation_arrays(dem: D.ArrayLike, nodata: Optional[float]
                                        csx: float = 1.0, csy: float = 1.0,
                                        positive_only: bool = True, validate: bool = True,
                                        out_direction: Optional[np.ndarray] = None,
-                                       out_accumulation: Optional[np.ndarray] = None):
+                                       out_accumulation: Optional[np.ndarray] = None,
+                                       method: str = "auto"):
     """Array-level ``flow_direction_accumulation``.
 
     Returns ``(direction int8, accumulation float64)``: GRASS codes 1..8 (1 = NE,
@@ -94,6 +120,12 @@ def flow_direction_accumulation_arrays(dem: D.ArrayLike, nodata: Optional[float]
     numpy in -> numpy out; CUDA tensor in -> CUDA tensors out.  ``out_direction``
     / ``out_accumulation`` (host arrays, ideally page-locked) receive the results
     without an intermediate copy.
+
+    ``method``: "auto" counts pits and ties first and takes the one-pass local-rule kernel
+    when the DEM is hydrologically conditioned (pit-free, tie-free after GRASS's millimetre
+    rounding), else the general kernel, which reproduces r.watershed's search on any DEM
+    (equal elevations, flats, depressions) in parallel rounds; "local" / "general" force one
+    ("local" raises ``ValueError`` on an unconditioned DEM unless ``validate=False``).
     """
     dev = D.require_cuda()
     on_host = not isinstance(dem, torch.Tensor)
@@ -101,15 +133,25 @@ def flow_direction_accumulation_arrays(dem: D.ArrayLike, nodata: Optional[float]
     rows, cols = int(a.shape[0]), int(a.shape[1])
     if rows == 0 or cols == 0:
         raise ValueError("empty raster")
+    if method not in ("auto", "local", "general"):
+        raise ValueError(f"unknown method {method!r}")
     buf, ld = D.upload(a, torch.float32, 4, dev)
-    if validate:
+    general = method == "general"
+    if method != "general" and (validate or method == "auto"):
         pits, ties = _validate(buf, ld, rows, cols, nodata, dev)
         if pits or ties:
-            raise ValueError(
-                f"DEM is not hydrologically conditioned ({pits} pits, {ties} cells with "
-                "tied elevations after GRASS mm rounding); hydrotools.cuda reproduces "
-                "r.watershed only on pit-free, tie-free DEMs and has no CPU fallback")
-    packed, pld = d8(buf, ld, rows, cols, nodata, csx, csy)
+            if method == "local":
+                raise ValueError(
+                    f"DEM is not hydrologically conditioned ({pits} pits, {ties} cells with "
+                    "tied elevations after GRASS mm rounding): the local-rule kernel does "
+                    "not apply; use method='auto' or 'general'")
+            general = True
+    if general:
+        packed, pld, info = d8_general(buf, ld, rows, cols, nodata, csx, csy)
+        LAST_STATS.clear()
+        LAST_STATS.update(info)
+    else:
+        packed, pld = d8(buf, ld, rows, cols, nodata, csx, csy)
     ws = _workspace(rows, cols, dev)
     acc, ald, dout, dld = accumulate(packed, pld, rows, cols, N.MODE_COUNT, want_dir=True, ws=ws)
     if not positive_only:

@@ -85,6 +85,23 @@ int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,
                                    int halo_bot, unsigned long long *counts3,
                                    void *stream);
 
+/* ---- the same for ANY DEM: equal elevations, flats, depressions ------------------
+ * r.watershed's least-cost search (heap keyed by elevation, first-in-first-out among
+ * equals; /root/reference/src/hydrotools/watershed.py:64-75 on a raw DEM such as the
+ * reference's own tests/data-files/dem.tif) reproduced bit for bit in parallel rounds:
+ * priority-flood levels by relaxation, then every cell's direction from the cells that
+ * pop before it; the cells of a depression are replayed sequentially by the thread of the
+ * cell that enters it (csrc/ht_astar_rules.h).  Whole rasters only (no row bands), fewer
+ * than 2^31 cells.  Synchronous: host loops read a device counter per round.
+ * stats8_host (may be NULL): [0] rounds, [1] depression episodes, [2] cells of the largest,
+ * [3] depression cells, [4] fill passes, [5] generation sweeps, [6] cells outside the
+ * supported elevation range (|z| >= 16 777 m; the result is then not valid), [7] errors. */
+size_t ht_d8_general_workspace_bytes(int64_t rows, int64_t cols);
+int ht_d8_general_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_nodata,
+                      float nodata, double ewres, double nsres, uint8_t *packed,
+                      int64_t packed_ld, void *ws, size_t ws_bytes, long long *stats8_host,
+                      void *stream);
+
 /* GRASS int8 codes (-128 = NULL) <-> packed byte; used for direction rasters that
  * come from disk (FlowAccumulation(direction),
  * /root/reference/src/hydrotools/watershed.py:329-339).  A code 1..8 whose

@@ -63,6 +63,8 @@ def lib():
             C.c_float, f32p]
         L.ora_synth_weight.argtypes = [
             C.c_uint64, C.c_int64, C.c_int64, C.c_int64, f32p]
+        L.ora_fill_mm.argtypes = [f32p, C.c_int64, C.c_int64, C.c_int, C.c_float,
+                                  np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")]
         L.ora_alt_from_f32.argtypes = [C.c_float]
         L.ora_alt_from_f32.restype = C.c_int32
         _lib = L
@@ -117,6 +119,24 @@ def condition_by_rank(dem, nodata=None, ewres=1.0, nsres=1.0):
     if rc:
         raise MemoryError("oracle conditioning failed")
     return out
+
+
+ALT_NULL = 0x7FFFFFFF
+
+
+def fill(dem, nodata=None):
+    """Priority-flood fill in GRASS integer millimetres, seeded like r.watershed's A*
+    (border and NULL-adjacent cells).  Returns (W int32 [ALT_NULL = NULL], filled DEM
+    float32 in metres with NULLs kept)."""
+    dem = _dem(dem)
+    has, nd = _nd(nodata)
+    w = np.empty(dem.shape, np.int32)
+    if lib().ora_fill_mm(dem, dem.shape[0], dem.shape[1], has, nd, w):
+        raise MemoryError("oracle fill failed")
+    out = (w.astype(np.float64) / 1000.0).astype(np.float32)
+    null = w == ALT_NULL
+    out[null] = dem[null]
+    return w, out
 
 
 def gdaldem(dem, nodata=None, ewres=1.0, nsres=1.0, scale=1.0, percent=False, threads=1):

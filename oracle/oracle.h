@@ -28,6 +28,11 @@ int ora_condition_by_rank(const float *dem, int64_t rows, int64_t cols,
                           int has_nodata, float nodata, double ewres,
                           double nsres, float *out);
 
+/* fill.c */
+#define ORA_ALT_NULL 0x7FFFFFFF
+int ora_fill_mm(const float *dem, int64_t rows, int64_t cols, int has_nodata,
+                float nodata, int32_t *w_out);
+
 /* gdaldem.c */
 int ora_gdaldem(const float *dem, int64_t rows, int64_t cols, int has_nodata,
                 float nodata, double ewres, double nsres, double scale,

@@ -143,7 +143,7 @@ def test_bands_weighted(hc):
     np.testing.assert_allclose(acc[m], exp[m], rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("cuts", [[0, 100, 333, 500], [0, 64, 65, 300, 500], [0, 500]])
+@pytest.mark.parametrize("cuts", [[0, 100, 333, 500], [0, 64, 66, 300, 500], [0, 500]])
 def test_bands_stored_direction(hc, golden, cuts):
     """Row a3 sharded: accumulation over a STORED direction raster in row bands equals the
     unsharded function and plain oracle.flowacc (r.flowaccumulation semantics: every cell

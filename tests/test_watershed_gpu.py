@@ -36,13 +36,74 @@ def test_conditioned_bundled_dem(hc, golden):
     np.testing.assert_array_equal(signed < 0, neg)
 
 
-def test_bundled_dem_is_refused_unconditioned(hc, golden):
-    nd = float(golden["dem_nodata"])
+def test_bundled_dem_raw(hc, golden):
+    """BASELINE.json configs[0]: the reference's own fixture (tests/data-files/dem.tif,
+    /root/reference/tests/test_watershed.py:10-16), RAW -- 2 326 pits, 30 950 tie cells, a
+    quarter of the cells inside depressions -- bit-exact against the oracle and the
+    committed golden vectors."""
+    nd, res = float(golden["dem_nodata"]), float(golden["res"])
     pits, ties = hc.validate_conditioned(golden["dem"], nd)
     assert (pits, ties) == oracle.check_conditioned(golden["dem"], nd)
     assert pits == 2326
     with pytest.raises(ValueError, match="not hydrologically conditioned"):
-        hc.flow_direction_accumulation_arrays(golden["dem"], nodata=nd, csx=5.0, csy=5.0)
+        hc.flow_direction_accumulation_arrays(golden["dem"], nodata=nd, csx=res, csy=res, method="local")
+    fd, fa = check_fd_fa(hc, golden["dem"], nd, res, res)
+    np.testing.assert_array_equal(fd, golden["fd"])
+    np.testing.assert_array_equal(np.nan_to_num(fa, nan=-1).astype(np.float32),
+                                  np.nan_to_num(golden["fa"], nan=-1))
+    check_fd_fa(hc, golden["dem"], nd, res, res, positive_only=False)
+    from hydrotools.cuda import watershed as W
+    assert W.LAST_STATS["episodes"] > 100 and W.LAST_STATS["errors"] == 0
+
+
+def _fbm(n, m, seed, hurst=0.8):
+    rng = np.random.default_rng(seed)
+    fy, fx = np.fft.fftfreq(n)[:, None], np.fft.fftfreq(m)[None, :]
+    f = np.sqrt(fx * fx + fy * fy)
+    f[0, 0] = 1
+    z = np.fft.ifft2((rng.normal(size=(n, m)) + 1j * rng.normal(size=(n, m))) / f ** (hurst + 1)).real
+    return (z - z.min()) / (z.max() - z.min())
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_general_path_random(hc, case):
+    """The general kernel on DEMs full of ties, flats, pits and NULL blobs (integer-valued
+    noise; spectral fBm surfaces rounded to cm / dm), square and anisotropic cells."""
+    rng = np.random.default_rng(100 + case)
+    if case < 4:
+        r, c = rng.integers(3, 150, 2)
+        dem = rng.integers(0, [3, 6, 30, 1000][case], (r, c)).astype(np.float32)
+    else:
+        n, m, scale, dec = [(300, 400, 500.0, 2), (500, 500, 50.0, 1), (350, 450, 2000.0, 3),
+                            (250, 250, 5.0, 0)][case - 4]
+        dem = (_fbm(n, m, case) * scale).round(dec).astype(np.float32)
+    if case % 2:
+        for _ in range(10):
+            r0, c0 = rng.integers(0, dem.shape[0]), rng.integers(0, dem.shape[1])
+            dem[r0:r0 + rng.integers(1, 12), c0:c0 + rng.integers(1, 12)] = ND
+    csx, csy = [(10.0, 10.0), (3.0, 4.0), (4.0, 3.0)][case % 3]
+    check_fd_fa(hc, dem, ND, csx, csy)
+    check_fd_fa(hc, dem, ND, csx, csy, positive_only=False)
+
+
+def test_general_equals_local_on_conditioned(hc):
+    """On a conditioned DEM both kernels are r.watershed: identical bytes."""
+    dem = oracle.synth_dem(77, 700, 900, with_nulls=True)
+    a = hc.flow_direction_accumulation_arrays(dem, nodata=ND, csx=10.0, csy=10.0, method="local")
+    b = hc.flow_direction_accumulation_arrays(dem, nodata=ND, csx=10.0, csy=10.0, method="general")
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_general_flat_and_lake(hc):
+    """A perfectly flat DEM (breadth-first from the border) and a single deep lake."""
+    flat = np.full((90, 130), 12.5, np.float32)
+    check_fd_fa(hc, flat, None, 10.0, 10.0)
+    lake = np.full((120, 100), 50.0, np.float32)
+    yy, xx = np.mgrid[0:120, 0:100]
+    lake -= np.maximum(0, 30 - np.hypot(yy - 60, xx - 50)).astype(np.float32)
+    lake += (yy * 0.01).astype(np.float32)
+    check_fd_fa(hc, lake, None, 10.0, 10.0)
 
 
 @pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (2, 2), (3, 3), (5, 7), (63, 65),
