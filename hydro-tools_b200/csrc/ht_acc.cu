@@ -372,7 +372,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // sm_100a (SASS ATOMS.CAST.SPIN.64); 32-bit integer adds are native (ATOMS.ADD).  So
 // the weights are quantised once and every sum downstream is integer arithmetic:
 //   * global unit 2^-sg, sg = G_BITS - ilogb(largest |weight| of the raster): the
-//     largest weight is ~2^61 units, a sum over 2^34 cells still fits 128 bits;
+//     largest weight is ~2^90 units, a sum over 2^34 cells still fits 128 bits;
 //   * stage A works in a per-tile unit 2^(et - sg), et >= 0 chosen so that the tile's
 //     largest weight is < 2^Q_BITS units: tile-local sums fit 64 bits and live in
 //     shared memory as two 32-bit words (native atomic add, carry handed on);
@@ -386,7 +386,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // resolved inflow along the entry paths with walkers, like the count mode.
 // ---------------------------------------------------------------------------
 constexpr int Q_BITS = 48;
-constexpr int G_BITS = 61;
+constexpr int G_BITS = 90;
 
 __device__ __forceinline__ int scale_exp_of(unsigned gmax_bits)
 {

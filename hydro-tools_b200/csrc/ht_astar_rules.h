@@ -327,14 +327,20 @@ HT_HD bool heap_less(const HeapItem &a, const HeapItem &b)
     return a.alt != b.alt ? a.alt < b.alt : a.added < b.added;
 }
 
+// 8-ary heap: a sift-down level costs one round of independent loads (the eight children
+// are contiguous) instead of two dependent ones per binary level -- the episode is one
+// thread chasing global-memory latency
+constexpr int HEAP_ARITY = 8;
+
 HT_D void heap_push(HeapItem *h, int32_t &n, HeapItem v)
 {
     int32_t i = n++;
     while (i > 0) {
-        const int32_t p = (i - 1) / 2;
-        if (!heap_less(v, h[p]))
+        const int32_t p = (i - 1) / HEAP_ARITY;
+        const HeapItem hp = h[p];
+        if (!heap_less(v, hp))
             break;
-        h[i] = h[p];
+        h[i] = hp;
         i = p;
     }
     h[i] = v;
@@ -346,13 +352,22 @@ HT_D HeapItem heap_pop(HeapItem *h, int32_t &n)
     const HeapItem v = h[--n];
     int32_t i = 0;
     for (;;) {
-        int32_t l = 2 * i + 1, r = l + 1, m;
-        if (l >= n)
+        const int32_t first = HEAP_ARITY * i + 1;
+        if (first >= n)
             break;
-        m = (r < n && heap_less(h[r], h[l])) ? r : l;
-        if (!heap_less(h[m], v))
+        const int32_t last = first + HEAP_ARITY < n ? first + HEAP_ARITY : n;
+        int32_t m = first;
+        HeapItem hm = h[first];
+        for (int32_t c = first + 1; c < last; c++) {
+            const HeapItem hc = h[c];
+            if (heap_less(hc, hm)) {
+                hm = hc;
+                m = c;
+            }
+        }
+        if (!heap_less(hm, v))
             break;
-        h[i] = h[m];
+        h[i] = hm;
         i = m;
     }
     if (n > 0)

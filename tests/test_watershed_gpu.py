@@ -56,7 +56,7 @@ def test_bundled_dem_raw(hc, golden):
     assert W.LAST_STATS["episodes"] > 100 and W.LAST_STATS["errors"] == 0
 
 
-def _fbm(n, m, seed, hurst=0.8):
+def _fbm_unit(n, m, seed, hurst=0.8):
     rng = np.random.default_rng(seed)
     fy, fx = np.fft.fftfreq(n)[:, None], np.fft.fftfreq(m)[None, :]
     f = np.sqrt(fx * fx + fy * fy)
@@ -76,7 +76,7 @@ def test_general_path_random(hc, case):
     else:
         n, m, scale, dec = [(300, 400, 500.0, 2), (500, 500, 50.0, 1), (350, 450, 2000.0, 3),
                             (250, 250, 5.0, 0)][case - 4]
-        dem = (_fbm(n, m, case) * scale).round(dec).astype(np.float32)
+        dem = (_fbm_unit(n, m, case) * scale).round(dec).astype(np.float32)
     if case % 2:
         for _ in range(10):
             r0, c0 = rng.integers(0, dem.shape[0]), rng.integers(0, dem.shape[1])
@@ -226,6 +226,18 @@ def test_flowacc_weight_ranges(hc, case):
     if case == "signed":  # cancellation: compare against the magnitude that flowed in
         mag = oracle.flowacc(fd, np.abs(we), wnd)
         assert np.max(np.abs(got[m] - exp[m]) / np.maximum(mag[m], 1e-30)) < 1e-12
+    elif case == "tiny_and_huge":
+        # the documented bound of the fixed-point sums: every weight is quantised to 2^-49 of
+        # the largest weight of its 64 x 64 tile, so a sum is off by at most that per cell
+        # upstream; relative 1e-5 holds wherever the weights of a tile span < 9 decades
+        cnt = oracle.flowacc(fd)
+        assert np.all(np.abs(got[m] - exp[m]) <= 2.0 ** -48 * np.nanmax(np.abs(we)) * cnt[m])
+        far = np.zeros(fd.shape, bool)
+        far[:, :128] = True  # tiles that hold tiny weights only ...
+        only_tiny = m & far & (exp < 1e-3)  # ... and cells that received nothing from the huge half
+        np.testing.assert_allclose(got[only_tiny], exp[only_tiny], rtol=1e-9, atol=0)  # tile unit, not the global one
+        big = m & (exp > 1.0)
+        np.testing.assert_allclose(got[big], exp[big], rtol=1e-9, atol=0)
     else:
         np.testing.assert_allclose(got[m], exp[m], rtol=1e-9, atol=0)
 
