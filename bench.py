@@ -464,6 +464,7 @@ def run_product(args):
     value = total_rows * cols / (ms * 1e-3) / 1e9
 
     # ---- end to end through the public API: pinned host in, host out
+    numa = D.bind_to_gpu_numa_node(local_rank)  # staging buffers on the GPU's own NUMA node
     host_dem = torch.empty((rows, cols), dtype=torch.float32, pin_memory=True)
     host_dem.copy_(engine.dem_view())
     out_fd = torch.empty((rows, cols), dtype=torch.int8, pin_memory=True)
@@ -505,10 +506,39 @@ def run_product(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    # what the host link can do with exactly these buffers: H2D of the DEM and D2H of both
+    # results at the same time (full duplex), every rank at once -- the floor of a step that
+    # has to move 13 B/cell over PCIe
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    tmp_dem = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    fd_dev, fa_dev = engine.results()
+
+    def link_step():
+        with torch.cuda.stream(s_in):
+            tmp_dem.copy_(host_dem, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            out_fd.copy_(fd_dev, non_blocking=True)
+            out_fa.copy_(fa_dev, non_blocking=True)
+        torch.cuda.synchronize()
+    link_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        link_step()
+    barrier()
+    link = (time.perf_counter() - t0) / 3
+    t = torch.tensor([link], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    link = float(t.item())
+    del tmp_dem
     e2e = {"value": total_rows * cols / dt / 1e9, "unit": UNIT,
            "h2d_bytes_per_step": rows * cols * 4 * world, "d2h_bytes_per_step": rows * cols * 9 * world,
            "ms_per_step": dt * 1e3, "steps": n_e2e, "api": api,
-           "note": "bound by PCIe: 13 B/cell cross the host link every step"}
+           "note": "bound by PCIe: 13 B/cell cross the host link every step",
+           "hostlink_floor_ms": link * 1e3,
+           "hostlink_gbs_aggregate": rows * cols * 13 * world / link / 1e9,
+           "frac_of_hostlink": link / dt, "numa": numa}
     # the e2e result must be the same answer
     fd_dev, fa_dev = engine.results()
     assert torch.equal(out_fd.to(dev), fd_dev) and torch.equal(out_fa.to(dev), fa_dev)

@@ -51,6 +51,7 @@ struct D8Args {
     int64_t rows, cols;       // owned rows, columns
     int64_t row0, total_rows; // position of owned row 0 in the whole raster
     int halo_top, halo_bot;   // rows available above / below (0 or >= 2)
+    int ring_top, ring_bot;   // also store the packed byte of row -1 / row `rows` (neighbour band's edge row)
     int tiles_x, tiles_y;
     int has_nodata;
     float nodata;
@@ -329,7 +330,7 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
         // plain tile: nothing but valid cells in the box, no raster border in the
         // ring, and not a tile row that also stores a neighbour band's halo row
         const bool framed = yy_top < 0 && xx_left < 0 && yy_bot >= DH && xx_right >= DW &&
-                            !(ty == 0 && p.halo_top) && !(ty == p.tiles_y - 1 && p.halo_bot) &&
+                            !(ty == 0 && p.ring_top) && !(ty == p.tiles_y - 1 && p.ring_bot) &&
                             y0 + TH <= p.rows && x0 + TW <= p.cols;
         const bool plain = !__syncthreads_or(saw_invalid) && framed && !VALIDATE;
 
@@ -442,7 +443,7 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
                 const int yy = item >> 3, seg = item & 7;
                 const int64_t lr = y0 - 1 + yy;
                 const bool own = yy >= 1 && yy <= TH && lr < p.rows;
-                const bool halo_row = (lr == -1 && p.halo_top) || (lr == p.rows && p.halo_bot);
+                const bool halo_row = (lr == -1 && p.ring_top) || (lr == p.rows && p.ring_bot);
                 const int64_t gc = x0 + seg * 16;
                 if (!(own || halo_row) || gc >= p.cols)
                     continue;
@@ -498,6 +499,8 @@ int setup(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_noda
     p.rows = rows; p.cols = cols; p.row0 = row0; p.total_rows = total_rows;
     p.halo_top = halo_top > 2 ? 2 : halo_top;
     p.halo_bot = halo_bot > 2 ? 2 : halo_bot;
+    p.ring_top = p.halo_top ? 1 : 0;
+    p.ring_bot = p.halo_bot ? 1 : 0;
     p.tiles_x = ht::cdiv(cols, TW); p.tiles_y = ht::cdiv(rows, TH);
     p.has_nodata = has_nodata ? 1 : 0;
     p.nodata = nodata;
@@ -528,10 +531,15 @@ int launch(const CUtensorMap &map, const D8Args &p, cudaStream_t st)
 
 } // namespace
 
-extern "C" int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld,
-                         int has_nodata, float nodata, double ewres, double nsres,
-                         int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
-                         uint8_t *packed, int64_t packed_ld, void *stream)
+// A run of rows of a band: like ht_d8_f32, but the packed byte of the row above / below the
+// run is stored only on request (ring_top / ring_bot) -- a row-band rank computes its
+// interior rows while the halo rows of its neighbours are still in flight, then the first
+// and last tile rows, and only those two calls also store the neighbours' edge rows.
+extern "C" int ht_d8_part_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld,
+                              int has_nodata, float nodata, double ewres, double nsres,
+                              int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                              int ring_top, int ring_bot, uint8_t *packed, int64_t packed_ld,
+                              void *stream)
 {
     if (rows == 0 || cols == 0)
         return HT_OK;
@@ -541,12 +549,23 @@ extern "C" int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t l
                    halo_top, halo_bot, p, map);
     if (rc)
         return rc;
-    if (!packed || packed_ld < cols)
+    if (!packed || packed_ld < cols || (ring_top && !halo_top) || (ring_bot && !halo_bot))
         return HT_ERR_ARG;
     if (((uintptr_t)packed & 15) || (packed_ld & 15))
         return HT_ERR_ALIGN;
     p.packed = packed; p.packed_ld = packed_ld;
+    p.ring_top = ring_top ? 1 : 0;
+    p.ring_bot = ring_bot ? 1 : 0;
     return launch<false>(map, p, (cudaStream_t)stream);
+}
+
+extern "C" int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld,
+                         int has_nodata, float nodata, double ewres, double nsres,
+                         int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                         uint8_t *packed, int64_t packed_ld, void *stream)
+{
+    return ht_d8_part_f32(dem, rows, cols, ld, has_nodata, nodata, ewres, nsres, row0, total_rows,
+                          halo_top, halo_bot, halo_top != 0, halo_bot != 0, packed, packed_ld, stream);
 }
 
 extern "C" int ht_d8_validate_conditioned_f32(const float *dem, int64_t rows, int64_t cols,

@@ -125,3 +125,45 @@ def download(view: torch.Tensor, out: Optional[np.ndarray] = None) -> np.ndarray
 
 def nodata_args(nodata: Optional[float]) -> Tuple[int, float]:
     return (0, 0.0) if nodata is None else (1, float(nodata))
+
+
+def bind_to_gpu_numa_node(index: Optional[int] = None) -> dict:
+    """Run this process (and place the pinned host buffers it allocates from now on) on the
+    NUMA node the GPU hangs off.  With one process per GPU on a two-socket box, staging
+    buffers that all sit on node 0 make half of the GPUs copy across the socket link and
+    all of them share one memory controller.  Best effort: needs sysfs and permission to
+    change affinity / memory policy; returns what was done."""
+    import ctypes
+    import os
+    info = {"node": None, "cpus_bound": False, "mempolicy": False}
+    try:
+        idx = torch.cuda.current_device() if index is None else index
+        import pynvml
+        pynvml.nvmlInit()
+        # NVML counts physical devices; CUDA_VISIBLE_DEVICES may renumber
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[idx]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else idx
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return info
+        info["node"] = node
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        usable = cpus & os.sched_getaffinity(0)
+        if usable:
+            os.sched_setaffinity(0, usable)
+            info["cpus_bound"] = True
+        # MPOL_PREFERRED (1): allocate on `node` when possible (syscall 238 = set_mempolicy)
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL(None, use_errno=True)
+        if libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask))) == 0:
+            info["mempolicy"] = True
+    except Exception as exc:  # no sysfs / NVML / permission: leave placement to the OS
+        info["error"] = f"{type(exc).__name__}: {exc}"[:120]
+    return info

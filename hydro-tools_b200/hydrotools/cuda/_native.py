@@ -49,6 +49,8 @@ SIGNATURES = {
                                   _i64, _int, _int, _p, C.c_size_t, _p],
     "ht_d8_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _i64, _i64, _int, _int,
                   _p, _i64, _p],
+    "ht_d8_part_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _i64, _i64, _int, _int,
+                       _int, _int, _p, _i64, _p],
     "ht_d8_validate_conditioned_f32": [_p, _i64, _i64, _i64, _int, _f32, _i64, _i64, _int,
                                        _int, _p, _p],
     "ht_d8_general_f32": [_p, _i64, _i64, _i64, _int, _f32, _f64, _f64, _p, _i64, _p, C.c_size_t,

@@ -75,6 +75,7 @@ class BandEngine:
         self.rows, self.cols, self.total_rows = rows, cols, total_rows
         self.group = group
         self.launches = 0
+        self._halo_buf = {}
         if band is None:
             if row0 is None:
                 row0 = rank * rows if world > 1 else 0
@@ -105,20 +106,36 @@ class BandEngine:
         return int(c[0]), int(c[1])
 
     # ----------------------------------------------------------------- comm
-    def exchange_halos(self, depth: int):
+    def exchange_halos(self, depth: int, async_op: bool = False):
         """`depth` DEM rows to / from each band neighbour.  One all-gather of every
         band's first and last `depth` rows (2 * depth * cols * 4 B per band): a single
         collective costs less than two send/recv pairs, and over NVSwitch the extra
-        rows are free."""
+        rows are free.  With ``async_op`` the collective is only enqueued (on NCCL's
+        stream); the returned callable waits for it and places the rows."""
         band, P = self.band, self.world
-        send = torch.stack([band.edge_rows(top=True, depth=depth),
-                            band.edge_rows(top=False, depth=depth)])  # [2, depth, cols]
-        every = torch.empty((P,) + tuple(send.shape), dtype=send.dtype, device=send.device)
-        dist.all_gather_into_tensor(every.view(P * 2, depth, self.cols), send, group=self.group)
-        if self.rank > 0:
-            band.set_halo_rows(top=True, rows=every[self.rank - 1, 1])
-        if self.rank < P - 1:
-            band.set_halo_rows(top=False, rows=every[self.rank + 1, 0])
+        if hasattr(band, "pack_edge_rows"):
+            send = band.pack_edge_rows(depth)  # preallocated [2, depth, cols]
+        else:
+            send = torch.stack([band.edge_rows(top=True, depth=depth),
+                                band.edge_rows(top=False, depth=depth)])  # [2, depth, cols]
+        key = (depth, send.dtype)
+        every = self._halo_buf.get(key)
+        if every is None:
+            every = torch.empty((P,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+            self._halo_buf[key] = every
+        work = dist.all_gather_into_tensor(every.view(P * 2, depth, self.cols), send, group=self.group,
+                                           async_op=async_op)
+
+        def finish():
+            if async_op:
+                work.wait()
+            if self.rank > 0:
+                band.set_halo_rows(top=True, rows=every[self.rank - 1, 1])
+            if self.rank < P - 1:
+                band.set_halo_rows(top=False, rows=every[self.rank + 1, 0])
+        if async_op:
+            return finish
+        finish()
 
     # ----------------------------------------------------------------- hot path
     def flow_direction_accumulation(self, mode: int = 0, positive_only: bool = True):
@@ -128,9 +145,19 @@ class BandEngine:
         at edge cells and below cells whose sign r.watershed flipped -- a second
         sharded accumulation over the taint flags decides that."""
         band = self.band
-        if self.world > 1:
-            self.exchange_halos(2)
-        band.direction()
+        if self.world > 1 and hasattr(band, "direction_part") and self.rows >= 4 * band.D8_TILE_ROWS:
+            # the interior rows need no halo: their D8 tiles run while the two halo rows of
+            # each neighbour are in flight; the first and last tile rows follow the exchange
+            work = self.exchange_halos(2, async_op=True)
+            e = band.D8_TILE_ROWS
+            band.direction_part(e, self.rows - e)
+            work()
+            band.direction_part(0, e)
+            band.direction_part(self.rows - e, self.rows)
+        else:
+            if self.world > 1:
+                self.exchange_halos(2)
+            band.direction()
         self.accumulate(mode)
         if not positive_only:
             band.stash_accumulation()
@@ -301,6 +328,7 @@ class CudaBand:
         self._tmp = None
         self._acc2 = None
         self._mode = 0
+        self._edge_buf = {}
 
     def _wsm(self, mode):
         """Workspace of `mode` (the weighted one is allocated on first use)."""
@@ -385,6 +413,16 @@ class CudaBand:
         r0 = 2 if top else 2 + self.rows - depth
         return self.dem[r0:r0 + depth, :self.cols].contiguous()
 
+    def pack_edge_rows(self, depth):
+        """First and last `depth` rows in one preallocated [2, depth, cols] buffer."""
+        buf = self._edge_buf.get(depth)
+        if buf is None:
+            buf = torch.empty((2, depth, self.cols), dtype=torch.float32, device=self.dev)
+            self._edge_buf[depth] = buf
+        buf[0].copy_(self.dem[2:2 + depth, :self.cols])
+        buf[1].copy_(self.dem[2 + self.rows - depth:2 + self.rows, :self.cols])
+        return buf
+
     def set_halo_rows(self, top, rows):
         depth = rows.shape[0]
         r0 = 2 - depth if top else 2 + self.rows
@@ -404,6 +442,21 @@ class CudaBand:
         self.N.call("ht_d8_f32", self._dem0(), self.rows, self.cols, self.ld, has, nd, self.csx,
                     self.csy, self.row0, self.total_rows, self.htop, self.hbot, self._packed0(),
                     self.pld, self.D.stream_ptr())
+        self._launches += 1
+
+    D8_TILE_ROWS = 32  # tile height of d8_kernel (csrc/ht_d8.cu): part boundaries fall on tile rows
+
+    def direction_part(self, r_lo, r_hi):
+        """D8 of rows [r_lo, r_hi) of the band (multiples of D8_TILE_ROWS, or the band's ends).
+        Rows inside the band find their halo in the band itself; only the parts that touch a
+        neighbour band need its halo rows and store its edge row's packed byte."""
+        has, nd = self.D.nodata_args(self.nodata)
+        top = 2 if (r_lo > 0 or self.htop) else 0
+        bot = 2 if (r_hi < self.rows or self.hbot) else 0
+        self.N.call("ht_d8_part_f32", self._dem0() + r_lo * self.ld * 4, r_hi - r_lo, self.cols,
+                    self.ld, has, nd, self.csx, self.csy, self.row0 + r_lo, self.total_rows, top, bot,
+                    int(r_lo == 0 and self.htop > 0), int(r_hi == self.rows and self.hbot > 0),
+                    self._packed0() + r_lo * self.pld, self.pld, self.D.stream_ptr())
         self._launches += 1
 
     def _wargs(self, mode):

@@ -76,6 +76,13 @@ int ht_d8_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_
               float nodata, double ewres, double nsres, int64_t row0,
               int64_t total_rows, int halo_top, int halo_bot, uint8_t *packed,
               int64_t packed_ld, void *stream);
+/* a run of rows of a band: the packed byte of the row above / below the run is stored only
+ * with ring_top / ring_bot (a rank computes its interior rows while its neighbours' halo
+ * rows are in flight, then its first and last tile rows) */
+int ht_d8_part_f32(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_nodata,
+                   float nodata, double ewres, double nsres, int64_t row0,
+                   int64_t total_rows, int halo_top, int halo_bot, int ring_top,
+                   int ring_bot, uint8_t *packed, int64_t packed_ld, void *stream);
 /* counts3[0] = pits (non-seed cells without a strictly lower neighbour),
  * counts3[1] = cells whose 3x3 window holds two equal integer elevations,
  * counts3[2] = cells whose |elevation| >= 2^24 mm = 16 777 m (unsupported; clamped) */

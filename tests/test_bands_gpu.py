@@ -178,3 +178,27 @@ def test_bands_stored_direction(hc, golden, cuts):
             np.testing.assert_allclose(acc[m], exp[m], rtol=1e-12, atol=0)
             whole = hc.flow_accumulation_arrays(fd, weight)
             np.testing.assert_array_equal(acc, whole)  # exact fixed point: sharding changes nothing
+
+
+def test_direction_in_parts_equals_whole(hc):
+    """BandEngine computes a band's interior rows while the halo rows travel, then its first
+    and last tile rows (ht_d8_part_f32): the packed bytes equal the one-call result."""
+    from hydrotools.cuda import distributed as HD
+    dem = oracle.synth_dem(11, 700, 500, with_nulls=True)
+    lo, hi = 200, 500
+    outs = []
+    for parts in (False, True):
+        band = HD.CudaBand(hi - lo, 500, lo, 700, 10.0, 10.0, ND, has_above=True, has_below=True)
+        band.load(dem[lo:hi])
+        band.set_halo_rows(top=True, rows=torch.from_numpy(dem[lo - 2:lo]).cuda())
+        band.set_halo_rows(top=False, rows=torch.from_numpy(dem[hi:hi + 2]).cuda())
+        band.packed.zero_()
+        if parts:
+            e = band.D8_TILE_ROWS
+            band.direction_part(e, band.rows - e)
+            band.direction_part(0, e)
+            band.direction_part(band.rows - e, band.rows)
+        else:
+            band.direction()
+        outs.append(band.packed.clone())
+    assert torch.equal(outs[0], outs[1])
