@@ -463,6 +463,15 @@ def run_product(args):
     ms = float(t.item())
     value = total_rows * cols / (ms * 1e-3) / 1e9
 
+    # correctness of THIS run's result: acc == 1 + donors on every cell of every band
+    # (neighbour-band donors included) and terminal mass == cells
+    fd_dev, fa_dev = engine.results()
+    mb_ok, mb_term, mb_tot = mass_balance(fd_dev, fa_dev, rank, world, total_rows)
+    parity = {"bench_raster": {"acc_equals_one_plus_donors_everywhere": mb_ok,
+                               "terminal_cells": mb_term, "cells": mb_tot,
+                               "exact": mb_ok and mb_term == mb_tot}}
+    del fd_dev, fa_dev
+
     # ---- end to end through the public API: pinned host in, host out
     numa = D.bind_to_gpu_numa_node(local_rank)  # staging buffers on the GPU's own NUMA node
     host_dem = torch.empty((rows, cols), dtype=torch.float32, pin_memory=True)
@@ -571,18 +580,10 @@ def run_product(args):
     path_roofline = {"algorithmic_bytes_per_cell": 14, "achieved": path_gbs, "peak": peak,
                      "unit": "GB/s", "frac": path_gbs / peak}
 
-    # correctness of THIS run's result: acc == 1 + donors on every cell of every band
-    # (neighbour-band donors included) and terminal mass == cells
-    fd_dev, fa_dev = engine.results()
-    mb_ok, mb_term, mb_tot = mass_balance(fd_dev, fa_dev, rank, world, total_rows)
-    parity = {"bench_raster": {"acc_equals_one_plus_donors_everywhere": mb_ok,
-                               "terminal_cells": mb_term, "cells": mb_tot,
-                               "exact": mb_ok and mb_term == mb_tot}}
-
     cpu = None
     # configs[2]: fused slope + aspect + TRI on 32768^2; with N > 1 the same raster in N
     # row bands (strong scaling), halo rows exchanged inside the timed region
-    del engine, fd_dev, fa_dev
+    del engine
     torch.cuda.empty_cache()
     parity["oracle"] = oracle_parity_small(rank, world, dev)
     # row a3 on the bench raster (single GPU) / per band
