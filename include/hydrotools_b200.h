@@ -212,6 +212,39 @@ int ht_acc_apply_sign(double *acc, int64_t acc_ld, const double *taint_acc,
                       int64_t taint_ld, const uint8_t *packed, int64_t packed_ld,
                       int64_t rows, int64_t cols, void *stream);
 
+/* ---- downstream consumers of the direction grid -------------------
+ * fd: int8 GRASS codes (1 = NE ... 8 = E, <= 0 and -128 end a path).  All three synchronise
+ * the stream (pointer-jumping sweeps / an inlet count are read back).  Fewer than 2^31 cells.
+ * ws: ht_streams_workspace_bytes(rows, cols, max_window, max_inlets) bytes (0, 0 for labels
+ * and basin). */
+size_t ht_streams_workspace_bytes(int64_t rows, int64_t cols, int max_window, int64_t max_inlets);
+/* replaces the numba walker `_fa_label_task`
+ *   /root/reference/src/hydrotools/streams.py:320-388
+ * labels (uint32, 0 = no reach) number the connected runs of cells that hold one reach value
+ * (!= nodata) and are linked by the direction grid, in row-major order of their first cell. */
+int ht_reach_labels_i32(const int32_t *reaches, int64_t r_ld, const int8_t *fd, int64_t fd_ld,
+                        int64_t rows, int64_t cols, int32_t nodata, uint32_t *labels,
+                        int64_t l_ld, void *ws, size_t ws_bytes, void *stream);
+/* replaces the numba walker `_upstream_compute`
+ *   /root/reference/src/hydrotools/morphology.py:50-153 (upstream_stats, :292-360)
+ * streams: nonzero = stream cell.  From every inlet (stream cell no stream cell drains
+ * into) down the stream: out[cell] = mean of `values` over the cells of the path within
+ * `distance` map units upstream (fp64 running sum in the reference's order, stored fp32);
+ * where paths overlap the inlet latest in row-major order prevails, as in the reference.
+ * `out` must arrive filled (the reference starts from NaN); cells never visited keep it.
+ * max_window = ceil(distance / min(csx, csy)) + 2 (morphology.py:331). */
+int ht_upstream_mean_f64(const double *values, int64_t v_ld, const uint8_t *streams, int64_t s_ld,
+                         const int8_t *fd, int64_t fd_ld, int64_t rows, int64_t cols, double csx,
+                         double csy, double distance, int max_window, int64_t max_inlets,
+                         float *out, int64_t o_ld, void *ws, size_t ws_bytes,
+                         long long *ninlets_host, void *stream);
+/* replaces GRASS r.water.outlet (/root/reference/src/hydrotools/watershed.py:292-318):
+ * out = 1 where the cell's path passes through (outlet_row, outlet_col), the outlet
+ * included, else 0. */
+int ht_basin_u8(const int8_t *fd, int64_t fd_ld, int64_t rows, int64_t cols, int64_t outlet_row,
+                int64_t outlet_col, uint8_t *out, int64_t o_ld, void *ws, size_t ws_bytes,
+                void *stream);
+
 /* ---- interpolate.raster_filter / custom_raster_filter ------------------------
  * replaces the numba moving-window kernel `apply_filter` under
  *   da.map_overlap(depth, boundary=nan)
