@@ -269,7 +269,7 @@ def oracle_parity_small(rank, world, dev):
     import oracle
     w_all = oracle.synth_weight(5, total, cols)
     eng.load_direction(fd)
-    wsum = eng.flow_accumulation(torch.from_numpy(w_all[rank * rows:(rank + 1) * rows]).to(dev))
+    wsum = eng.flow_accumulation(torch.from_numpy(w_all[rank * rows:(rank + 1) * rows]).to(dev)).clone()
     cnt = eng.flow_accumulation(None)
 
     def gather(t):
@@ -339,6 +339,7 @@ def weighted_run(rank, world, rows, cols, peak, barrier, dev, steps=3):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    acc = acc.clone()  # the engine returns a view of its own buffer
     again = eng.flow_accumulation(wv)
     rep = torch.tensor([1.0 if torch.equal(again, acc) else 0.0], dtype=torch.float64, device=dev)
     if world > 1:

@@ -371,22 +371,29 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 // Shared-memory fp64 (and 64-bit integer) atomicAdd is a compare-and-swap loop on
 // sm_100a (SASS ATOMS.CAST.SPIN.64); 32-bit integer adds are native (ATOMS.ADD).  So
 // the weights are quantised once and every sum downstream is integer arithmetic:
-//   * global unit 2^-sg, sg = G_BITS - ilogb(largest |weight| of the raster): the
-//     largest weight is ~2^90 units, a sum over 2^34 cells still fits 128 bits;
+//   * global unit 2^-(sg + 24), sg = G_BITS - ilogb(largest |weight| of the raster): the
+//     largest weight is ~2^88 units, a sum over 2^34 cells still fits 128 bits; the low
+//     24 bits of every value are zero and carry the band-edge marks of a sharded run
+//     (as bits 40.. of the u64 counts do);
 //   * stage A works in a per-tile unit 2^(et - sg), et >= 0 chosen so that the tile's
 //     largest weight is < 2^Q_BITS units: tile-local sums fit 64 bits and live in
 //     shared memory as two 32-bit words (native atomic add, carry handed on);
 //   * flow that leaves a tile, the boundary graph (stage B) and stage C are 128-bit
 //     integers in the global unit (two native 64-bit global atomics with carry).
 // Integer addition is associative, so the result does not depend on the order of the
-// atomics: weighted accumulation is bit-reproducible from run to run.  Quantisation
-// error per weight <= 2^-(Q_BITS+1) of the tile's largest weight (and nothing for
-// weights within 2^Q_BITS of the raster's largest); the contract is 1e-5 relative.
+// atomics: weighted accumulation is bit-reproducible from run to run.  Quantisation:
+// every nonzero weight keeps at least Q_KEEP = 26 significant bits (relative error
+// <= 2^-27, below fp32's own resolution) as long as the weights of its 64 x 64 tile span
+// less than 2^(Q_BITS - Q_KEEP) = 4 million to one; beyond that the error is at most
+// 2^-(Q_BITS+1) of the tile's largest weight.  The contract is 1e-5 relative.
 // Stage A leaves the tile-local sums (int64, 8 B/cell) for stage C, which adds the
 // resolved inflow along the entry paths with walkers, like the count mode.
 // ---------------------------------------------------------------------------
-constexpr int Q_BITS = 48;
-constexpr int G_BITS = 90;
+constexpr int Q_BITS = 48; // at most: the tile's largest weight < 2^48 tile units (sums fit 64 bits)
+constexpr int Q_MIN = 30;  // at least
+constexpr int Q_KEEP = 26; // significant bits every nonzero weight of a tile keeps (fp32 has 24)
+constexpr int G_BITS = 64;
+constexpr int W_MARK_BITS = 24; // global-unit values are multiples of 2^24: band-edge marks ride below
 
 __device__ __forceinline__ int scale_exp_of(unsigned gmax_bits)
 {
@@ -408,10 +415,19 @@ weight_max_kernel(const float *w, int64_t w_ld, int64_t rows, int64_t cols, int 
                   unsigned *out_bits)
 {
     float m = 0.0f;
-    const int64_t n = rows * cols;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cols, c = i - r * cols;
+    // a warp reads 128 consecutive floats of a row as float4 when the row allows it
+    const bool vec = !((uintptr_t)w & 15) && !(w_ld & 3);
+    const int64_t quads = vec ? cols / 4 : 0;
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = gtid; i < rows * quads; i += gsize) {
+        const int64_t r = i / quads, q = i - r * quads;
+        const float4 v = *reinterpret_cast<const float4 *>(w + r * w_ld + 4 * q);
+        m = fmaxf(fmaxf(m, fabsf(clean_weight(v.x, has_wnd, wnd))), fabsf(clean_weight(v.y, has_wnd, wnd)));
+        m = fmaxf(fmaxf(m, fabsf(clean_weight(v.z, has_wnd, wnd))), fabsf(clean_weight(v.w, has_wnd, wnd)));
+    }
+    const int64_t tail = cols - 4 * quads; // columns the quads do not cover
+    for (int64_t i = gtid; i < rows * tail; i += gsize) {
+        const int64_t r = i / tail, c = 4 * quads + (i - r * tail);
         m = fmaxf(m, fabsf(clean_weight(w[r * w_ld + c], has_wnd, wnd)));
     }
     const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m)); // |x| bits order like x
@@ -440,7 +456,7 @@ constexpr int SMW_LUT = SMW_HI + T * T * 4;      // uint32[16] code -> pointer s
 constexpr int SMW_BAR = SMW_LUT + 64;            // mbarrier, counters, tile maximum
 constexpr int SMW_TOTAL = SMW_BAR + 32;
 
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 4)
 acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -453,6 +469,7 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMW_BAR);
     int *ctl = reinterpret_cast<int *>(smem_raw + SMW_BAR + 8); // [0] entries, [1] their place in the list
     unsigned *tmaxb = reinterpret_cast<unsigned *>(smem_raw + SMW_BAR + 16);
+    unsigned *tminb = reinterpret_cast<unsigned *>(smem_raw + SMW_BAR + 20);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -461,6 +478,7 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     if (tid == 0) {
         ctl[0] = 0;
         *tmaxb = 0u;
+        *tminb = 0x7F800000u;
         ht::mbar_init(&bar, 1);
         ht::fence_mbar_init();
         ht::mbar_expect_tx(&bar, RH * RP);
@@ -483,7 +501,7 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     unsigned low[CPT];
     {
         const unsigned cm = (lx == 0 ? EX_W : 0u) | (lx == tw - 1 ? EX_E : 0u) | (lx >= tw ? 0xFFFFu : 0u) | 1u;
-        float m = 0.0f;
+        float m = 0.0f, mn = __uint_as_float(0x7F800000u);
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             const int ly = ly0 + 4 * k;
@@ -493,19 +511,32 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
             if (b & HT_DIR_NULL)
                 wv[k] = 0.0f;
-            m = fmaxf(m, fabsf(wv[k]));
+            const float aw = fabsf(wv[k]);
+            m = fmaxf(m, aw);
+            mn = aw > 0.0f ? fminf(mn, aw) : mn;
             low[k] = 2u * (unsigned)(tid + k * THREADS) + (stop ? 0u : lut[code]);
             ptr16[tid + k * THREADS] = (uint16_t)low[k];
         }
         const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-        if (lane == 0 && wm)
+        const unsigned wn = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
+        if (lane == 0 && wm) {
             atomicMax(tmaxb, wm);
+            atomicMin(tminb, wn);
+        }
     }
     __syncthreads();
-    // per-tile unit: the tile's largest weight is < 2^Q_BITS units
+    // per-tile unit: fine enough that the tile's SMALLEST weight keeps Q_KEEP significant bits,
+    // never coarser than what lets its largest weight fit Q_BITS bits, never finer than the
+    // global unit; and not finer than needed -- sums below 2^32 units cost one shared atomic
+    // instead of two (a raster like precipitation, weights within a factor of two: Q_MIN bits)
     const int sg = scale_exp_of(*p.gmax_bits);
-    const float tmax = __uint_as_float(*tmaxb);
-    const int et = tmax > 0.0f ? max(0, ilogbf(tmax) + 1 + sg - Q_BITS) : 0;
+    const float tmax = __uint_as_float(*tmaxb), tmin = __uint_as_float(*tminb);
+    int et = 0;
+    if (tmax > 0.0f) {
+        const int span = ilogbf(tmax) - ilogbf(tmin);                   // >= 0
+        const int qbits = min(Q_BITS, max(Q_MIN, span + Q_KEEP));       // bits of the largest weight
+        et = max(0, ilogbf(tmax) + 1 + sg - qbits);
+    }
     const double sc = pow2d(sg - et);
     long long a[CPT];
 #pragma unroll
@@ -556,7 +587,7 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             if (val)
                 atomic_add_v(reinterpret_cast<i128 *>(p.base) +
                                  exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE)),
-                             shl_i64(val, et));
+                             shl_i64(val, et + W_MARK_BITS));
         }
         bool entry = false;
         if (per && !(b & HT_DIR_NULL)) {
@@ -660,7 +691,7 @@ acc_final_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             uint32_t wd[4][4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const i128 g = shl_i64(v[j], et);
+                const i128 g = shl_i64(v[j], et + W_MARK_BITS);
                 wd[0][j] = (uint32_t)g.lo; wd[1][j] = (uint32_t)(g.lo >> 32);
                 wd[2][j] = (uint32_t)g.hi; wd[3][j] = (uint32_t)((unsigned long long)g.hi >> 32);
             }
@@ -672,8 +703,10 @@ acc_final_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     }
     int ely = 0, elx = 0;
     i128 inflow(0);
-    if (perimeter_cell(tid, th, tw, ely, elx))
+    if (perimeter_cell(tid, th, tw, ely, elx)) {
         inflow = reinterpret_cast<const i128 *>(p.inflow)[(int64_t)tile * SLOTS + tid];
+        inflow.lo &= ~((1ull << W_MARK_BITS) - 1ull); // band-edge marks of a sharded run
+    }
     __syncthreads();
     ht::mbar_wait(&bar, 0);
 
@@ -711,7 +744,7 @@ acc_final_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     // ---- outputs: 4 cells per thread and pass, NaN where NULL
     if (!p.acc)
         return;
-    const double unit = pow2d(-sg);
+    const double unit = pow2d(-sg - W_MARK_BITS);
     double *accp = p.acc + (y0 + r0) * p.acc_ld + x0 + q4;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -975,7 +1008,12 @@ __device__ __forceinline__ unsigned long long masked_plus(unsigned long long old
     return (old & ((1ull << MARK_SHIFT) - 1ull)) + add;
 }
 __device__ __forceinline__ double masked_plus(double old, double add) { return old + add; }
-__device__ __forceinline__ i128 masked_plus(const i128 &old, const i128 &add) { return old + add; }
+__device__ __forceinline__ i128 masked_plus(const i128 &old, const i128 &add)
+{
+    return i128(old.lo & ~((1ull << 24) - 1ull), old.hi) + add; // W_MARK_BITS
+}
+__device__ __forceinline__ bool is_marked(unsigned long long v) { return (v >> MARK_SHIFT) != 0ull; }
+__device__ __forceinline__ bool is_marked(const i128 &v) { return (v.lo & ((1ull << 24) - 1ull)) != 0ull; }
 
 template <typename V>
 __global__ void __launch_bounds__(256, 4)
@@ -1088,10 +1126,11 @@ __global__ void append_range_kernel(int32_t *list, int *nlist, int32_t first, in
 // on or downstream of a band-edge cell, i.e. they are the only ones whose inflow
 // changes when the neighbour bands' deliveries come in.  They are closed under
 // next[]: a forest of their own, resolved with base = the imported flow.
-__global__ void marked_nodes_kernel(const unsigned long long *agg, const int32_t *list,
+template <typename V>
+__global__ void marked_nodes_kernel(const V *agg, const int32_t *list,
                                     const int *nlist, int32_t *list2, int *nlist2,
-                                    unsigned long long *base2, const unsigned long long *imp_top,
-                                    const unsigned long long *imp_bot, int64_t rows, int64_t cols,
+                                    V *base2, const V *imp_top,
+                                    const V *imp_bot, int64_t rows, int64_t cols,
                                     int tiles_x, int tiles_y)
 {
     const int na = *nlist;
@@ -1100,7 +1139,7 @@ __global__ void marked_nodes_kernel(const unsigned long long *agg, const int32_t
     for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < na; i0 += gridDim.x * blockDim.x) {
         const int i = i0 + lane;
         const int32_t u = i < na ? list[i] : 0;
-        const bool in = i < na && (agg[u] >> MARK_SHIFT) != 0ull;
+        const bool in = i < na && is_marked(agg[u]);
         const unsigned m = __ballot_sync(0xffffffffu, in);
         if (!m)
             continue;
@@ -1110,7 +1149,7 @@ __global__ void marked_nodes_kernel(const unsigned long long *agg, const int32_t
         at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
         if (in) {
             list2[at] = u;
-            unsigned long long b = 0ull;
+            V b(0);
             const int tile = u / SLOTS, k = u % SLOTS;
             if (tile < tiles_x * tiles_y) { // not a virtual slot
                 const int ty = tile / tiles_x, tx = tile % tiles_x;
@@ -1191,7 +1230,9 @@ __global__ void band_tables_w_kernel(const i128 *agg, const int32_t *root, int64
     const int last_h = (int)(rows - (int64_t)last_ty * T);
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols;
          c += (int64_t)gridDim.x * blockDim.x) {
-        const i128 up = agg[vfirst + c], dn = agg[vfirst + cols + c];
+        i128 up = agg[vfirst + c], dn = agg[vfirst + cols + c];
+        up.lo &= ~((1ull << W_MARK_BITS) - 1ull); // marks cleared
+        dn.lo &= ~((1ull << W_MARK_BITS) - 1ull);
         out[c] = (long long)up.lo;
         out[cols + c] = up.hi;
         out[2 * cols + c] = (long long)dn.lo;
@@ -1248,16 +1289,18 @@ __device__ __forceinline__ int64_t edge_slot(bool top, int64_t c, int64_t rows, 
 
 // count modes: tag the slots of the band's first / last row (where flow from a neighbour
 // band can come in); the mark rides through the resolve in the upper bits of the sums
-__global__ void mark_edges_kernel(unsigned long long *base0, int64_t rows, int64_t cols, int tiles_x,
-                                  int tiles_y, int top, int bot)
+// `words` = 64-bit words per value (1: u64 counts, mark 1 << 40; 2: 128-bit weighted sums, mark 1
+// in the low word, whose low 24 bits are free)
+__global__ void mark_edges_kernel(unsigned long long *base0, int words, unsigned long long mark,
+                                  int64_t rows, int64_t cols, int tiles_x, int tiles_y, int top, int bot)
 {
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols;
          c += (int64_t)gridDim.x * blockDim.x) {
         // a band of one tile row and height 1 has top == bottom slots; atomics keep both marks
         if (top)
-            atomicAdd(base0 + edge_slot(true, c, rows, tiles_x, tiles_y), 1ull << MARK_SHIFT);
+            atomicAdd(base0 + words * edge_slot(true, c, rows, tiles_x, tiles_y), mark);
         if (bot)
-            atomicAdd(base0 + edge_slot(false, c, rows, tiles_x, tiles_y), 1ull << MARK_SHIFT);
+            atomicAdd(base0 + words * edge_slot(false, c, rows, tiles_x, tiles_y), mark);
     }
 }
 
@@ -1488,7 +1531,7 @@ extern "C" int ht_acc_weight_max(const float *w, int64_t w_ld, int64_t rows, int
     if (rows == 0 || cols == 0)
         return HT_OK;
     const int64_t n = rows * cols;
-    const int grid = (int)min((int64_t)ht::kSMs * 8, (n + 255) / 256);
+    const int grid = (int)min((int64_t)ht::kSMs * 8, (n / 4 + 255) / 256 + 1);
     weight_max_kernel<<<grid, 256, 0, st>>>(w, w_ld, rows, cols, has_wnd, wnd, max_bits);
     HT_LAUNCH_CHECK();
     return HT_OK;
@@ -1584,8 +1627,10 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
 extern "C" int ht_acc_mark_edges(int64_t rows, int64_t cols, int mode, int halo_top, int halo_bot,
                                  void *ws, size_t ws_bytes, void *stream)
 {
-    if (rows <= 0 || cols <= 0 || mode == W_F32 || mode < 0 || mode > 2)
+    if (rows <= 0 || cols <= 0 || mode < 0 || mode > 2)
         return HT_ERR_ARG;
+    if (mode == W_F32 && 2 * cols >= (1ll << W_MARK_BITS))
+        return HT_ERR_ARG; // the marks of one band would overflow their 24 bits
     if (!halo_top && !halo_bot)
         return HT_OK;
     Workspace wk;
@@ -1593,8 +1638,8 @@ extern "C" int ht_acc_mark_edges(int64_t rows, int64_t cols, int mode, int halo_
     if (rc)
         return rc;
     mark_edges_kernel<<<ht::cdiv(cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        (unsigned long long *)wk.base0, rows, cols, ht::cdiv(cols, T), ht::cdiv(rows, T),
-        halo_top ? 1 : 0, halo_bot ? 1 : 0);
+        (unsigned long long *)wk.base0, mode == W_F32 ? 2 : 1, mode == W_F32 ? 1ull : 1ull << MARK_SHIFT,
+        rows, cols, ht::cdiv(cols, T), ht::cdiv(rows, T), halo_top ? 1 : 0, halo_bot ? 1 : 0);
     HT_LAUNCH_CHECK();
     return HT_OK;
 }
@@ -1625,31 +1670,39 @@ extern "C" int ht_acc_add_imports(int64_t rows, int64_t cols, int mode, const vo
     return HT_OK;
 }
 
-// Row-band sharding, count modes.  ht_acc_resolve must have run on a boundary graph
-// whose band-edge slots carried a mark (1 << 40 added to base0; ht_acc_mark_edges); `imp_top` /
-// `imp_bot` (cols values each, or NULL) are the flows the neighbour bands deliver
+// Row-band sharding.  ht_acc_resolve must have run on a boundary graph whose band-edge
+// slots carried a mark (ht_acc_mark_edges: 1 << 40 added to the u64 counts, 1 to the low
+// word of the 128-bit weighted sums); `imp_top` / `imp_bot` (cols values of the mode's
+// type each, or NULL) are the flows the neighbour bands deliver
 // into the cells of the band's first / last row.  Adds their effect to the resolved
 // inflow of every node downstream and clears the marks -- a resolve over the
 // marked nodes only instead of a second full one.
-extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
-                                    const unsigned long long *imp_top,
-                                    const unsigned long long *imp_bot, void *ws, size_t ws_bytes,
-                                    void *stream)
+extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode, const void *imp_top,
+                                    const void *imp_bot, void *ws, size_t ws_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (rows == 0 || cols == 0)
         return HT_OK;
-    if (mode == W_F32 || mode < 0 || mode > 2)
-        return HT_ERR_ARG; // marks need integer sums
+    if (mode < 0 || mode > 2)
+        return HT_ERR_ARG;
     Workspace wk;
     int rc = carve(ws, ws_bytes, rows, cols, mode, wk);
     if (rc)
         return rc;
     HT_CUDA_TRY(cudaMemsetAsync(wk.nlist2, 0, sizeof(int), st));
-    marked_nodes_kernel<<<ht::kSMs * 4, 256, 0, st>>>(
+    if (mode == W_F32) {
+        marked_nodes_kernel<i128><<<ht::kSMs * 4, 256, 0, st>>>(
+            (const i128 *)wk.aggB, wk.list, wk.nlist, wk.list2, wk.nlist2, (i128 *)wk.base2,
+            (const i128 *)imp_top, (const i128 *)imp_bot, rows, cols, ht::cdiv(cols, T), ht::cdiv(rows, T));
+        HT_LAUNCH_CHECK();
+        return launch_resolve<i128>(wk.base2, wk.next0, wk.nslots, wk.list2, wk.nlist2, wk.idmap, wk.ptrA,
+                                    wk.ptrB, wk.aggA, wk.arr0, wk.arr1, nullptr, nullptr, wk.aggB, nullptr,
+                                    wk.flags, nullptr, st, 1);
+    }
+    marked_nodes_kernel<unsigned long long><<<ht::kSMs * 4, 256, 0, st>>>(
         (const unsigned long long *)wk.aggB, wk.list, wk.nlist, wk.list2, wk.nlist2,
-        (unsigned long long *)wk.base2, imp_top, imp_bot, rows, cols, ht::cdiv(cols, T),
-        ht::cdiv(rows, T));
+        (unsigned long long *)wk.base2, (const unsigned long long *)imp_top,
+        (const unsigned long long *)imp_bot, rows, cols, ht::cdiv(cols, T), ht::cdiv(rows, T));
     HT_LAUNCH_CHECK();
     return launch_resolve<unsigned long long>(wk.base2, wk.next0, wk.nslots, wk.list2, wk.nlist2,
                                               wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,

@@ -190,16 +190,16 @@ class BandEngine:
         last flow_direction_accumulation() left on the device: ``weight`` = this rank's rows
         of the weight raster.  Returns this rank's rows of the fp64 sums."""
         band = self.band
-        if weight is None:  # cell counts ("modals", watershed.py:341-355)
-            band.stash_accumulation()
-            self.accumulate(band.N.MODE_COUNT, want_dir=False)
-            out = band.acc[:, :self.cols].clone()
-            band.unstash_accumulation()
-            return out
-        band.set_weight(weight, weight_nodata)
+        # the result lands in the band's second accumulation buffer and is returned as a view of
+        # it: valid until the next flow_accumulation / signed run of this engine (no copy of
+        # 8 B/cell inside the hot path)
         band.stash_accumulation()
-        self.accumulate(band.N.MODE_WEIGHTED)
-        out = band.acc[:, :self.cols].clone()
+        if weight is None:  # cell counts ("modals", watershed.py:341-355)
+            self.accumulate(band.N.MODE_COUNT, want_dir=False)
+        else:
+            band.set_weight(weight, weight_nodata)
+            self.accumulate(band.N.MODE_WEIGHTED)
+        out = band.acc[:, :self.cols]
         band.unstash_accumulation()
         return out
 
@@ -375,7 +375,15 @@ class CudaBand:
                        non_blocking=False)
 
     def set_weight(self, w, nodata=None):
-        self.weight, self.wld = self.D.upload(w, torch.float32, 4, self.dev)
+        """A float32 CUDA tensor whose rows are 16-byte aligned is used in place (it must stay
+        unchanged until the accumulation has run); anything else is copied to the device."""
+        a = self.D.as_2d(w)
+        if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float32 and a.stride(1) == 1
+                and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
+                and tuple(a.shape) == (self.rows, self.cols)):
+            self.weight, self.wld = a, int(a.stride(0))
+        else:
+            self.weight, self.wld = self.D.upload(a, torch.float32, 4, self.dev)
         self.wnd = nodata
 
     def dem_view(self):
@@ -515,7 +523,7 @@ class CudaBand:
     MARK = 1 << 40  # band-edge mark in the u64 sums of the boundary graph (csrc/ht_acc.cu)
 
     def supports_delta(self, mode):
-        return mode != self.N.MODE_WEIGHTED
+        return True
 
     def mark_edges(self, mode=0):
         """After stage A: tag the slots of the band's first / last row (where flow from a
@@ -530,10 +538,11 @@ class CudaBand:
         """Second resolve of a sharded run, over the marked nodes only."""
         top = top.contiguous() if self.htop else None
         bot = bot.contiguous() if self.hbot else None
+        ws = self._wsm(mode)
         self.N.call("ht_acc_resolve_delta", self.rows, self.cols, mode,
                     top.data_ptr() if top is not None else None,
                     bot.data_ptr() if bot is not None else None,
-                    self.ws.data_ptr(), self.ws.numel(), self.D.stream_ptr())
+                    ws.data_ptr(), ws.numel(), self.D.stream_ptr())
         self._launches += 2
 
     def publish_tables(self, mode=0):

@@ -167,19 +167,18 @@ int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t
                  void *ws, size_t ws_bytes, void *stream);
 int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roots, void *ws,
                    size_t ws_bytes, int *rounds_dev, void *stream);
-/* row-band sharding, count modes, after ht_acc_local: tag the boundary-graph slots of the
- * band's first (halo_top) / last (halo_bot) row with a mark (1 << 40 added to their base0
- * entry) that rides through ht_acc_resolve to every node downstream */
+/* row-band sharding, after ht_acc_local: tag the boundary-graph slots of the band's first
+ * (halo_top) / last (halo_bot) row with a mark (1 << 40 added to the u64 counts; 1 added to
+ * the low word of the 128-bit weighted sums, whose low 24 bits are free) that rides through
+ * ht_acc_resolve to every node downstream */
 int ht_acc_mark_edges(int64_t rows, int64_t cols, int mode, int halo_top, int halo_bot,
                       void *ws, size_t ws_bytes, void *stream);
-/* row-band sharding, count modes: after ht_acc_resolve on a marked graph, add the effect of
- * the flows the neighbour bands deliver into the band's first / last row (imp_top /
- * imp_bot: cols values each, or NULL) and clear the marks -- a resolve over the
- * nodes downstream of the band edge instead of a second full one */
-int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode,
-                         const unsigned long long *imp_top,
-                         const unsigned long long *imp_bot, void *ws, size_t ws_bytes,
-                         void *stream);
+/* row-band sharding: after ht_acc_resolve on a marked graph, add the effect of the flows
+ * the neighbour bands deliver into the band's first / last row (imp_top / imp_bot: cols
+ * values of the mode's type each -- u64 or 128-bit -- or NULL) and clear the marks: a
+ * resolve over the nodes downstream of the band edge instead of a second full one */
+int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode, const void *imp_top,
+                         const void *imp_bot, void *ws, size_t ws_bytes, void *stream);
 /* row-band sharding, any mode: add the imported flows (cols values of the mode's type, u64
  * or 128-bit, or NULL) to the boundary graph; a second full ht_acc_resolve follows */
 int ht_acc_add_imports(int64_t rows, int64_t cols, int mode, const void *imp_top,

@@ -119,11 +119,13 @@ def test_bands_upward_flow(hc, delta):
     np.testing.assert_array_equal(fa, efa)
 
 
-def test_bands_weighted(hc):
+@pytest.mark.parametrize("delta", [False, True])
+def test_bands_weighted(hc, delta):
     dem = oracle.synth_dem(3, 500, 400, with_nulls=True)
     w = oracle.synth_weight(3, 500, 400)
     from hydrotools.cuda import _native as N
-    _, acc = run_bands(dem, [0, 100, 333, 500], ND, 10.0, 10.0, mode=N.MODE_WEIGHTED, weight=w)
+    _, acc = run_bands(dem, [0, 100, 333, 500], ND, 10.0, 10.0, mode=N.MODE_WEIGHTED, weight=w,
+                       delta=delta)
     # weighted accumulation follows r.watershed's graph here (edge cells do not pass
     # flow on), so the expectation is built from the oracle's directions with the
     # edge cells made terminal
@@ -168,7 +170,7 @@ def test_bands_stored_direction(hc, golden, cuts):
         for b, band in enumerate(bands):
             band.set_dir_halo(edges[b - 1][1] if b > 0 else None, edges[b + 1][0] if b < P - 1 else None)
             band.pack_direction()
-        _, acc = accumulate_bands(bands, mode, delta=(mode == N.MODE_COUNT and P > 1), direction=False)
+        _, acc = accumulate_bands(bands, mode, delta=P > 1, direction=False)
         exp = oracle.flowacc(fd, weight)
         np.testing.assert_array_equal(np.isnan(acc), np.isnan(exp))
         m = ~np.isnan(exp)

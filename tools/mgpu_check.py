@@ -33,7 +33,7 @@ for nulls in (False, True):
     gfs = [torch.empty_like(fs.contiguous()) for _ in range(world)]
     dist.all_gather(gfs, fs.contiguous())
     w_all = oracle.synth_weight(5, total, cols)
-    wsum = eng.flow_accumulation(torch.from_numpy(w_all[rank * rows:(rank + 1) * rows]).cuda())
+    wsum = eng.flow_accumulation(torch.from_numpy(w_all[rank * rows:(rank + 1) * rows]).cuda()).clone()
     gw = [torch.empty_like(wsum) for _ in range(world)]
     dist.all_gather(gw, wsum.contiguous())
     if rank == 0:
