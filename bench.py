@@ -359,6 +359,49 @@ def weighted_run(rank, world, rows, cols, peak, barrier, dev, steps=3):
                        "rel_diff": abs(term - tot) / max(abs(tot), 1e-300)}}
 
 
+def general_path_run(peak, dev, n=10000, sigma=0.3, steps=3):
+    """D8 direction of a RAW DEM through the general kernel chain
+    (ht_d8_general_f32: priority-flood levels, parallel rounds, depression episodes) --
+    the bench's fluvial terrain plus N(0, sigma) metres of noise, rounded to centimetres:
+    millions of pits and tie cells.  Followed by the usual accumulation; checked by mass
+    balance (the oracle comparison of this path is in the tests, up to 4000 x 4000)."""
+    import torch
+    from hydrotools.cuda import synth, watershed as W, _native as N
+    t, ld = synth.synth_dem(SEED, n, n)
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED)
+    for r0 in range(0, n, 2000):  # synthetic input, made on the device in slabs
+        v = t[r0:r0 + 2000, :n]
+        v.add_(torch.randn(v.shape, generator=g, device=dev) * sigma)
+        v.mul_(100.0).round_().div_(100.0)
+    pits, ties = W._validate(t, ld, n, n, None, dev)
+    ms_dir, info = [], None
+    for it in range(steps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        packed, pld, info = W.d8_general(t, ld, n, n, None, CSX, CSY)
+        torch.cuda.synchronize()
+        if it:
+            ms_dir.append((time.perf_counter() - t0) * 1e3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    acc, ald, dout, dld = W.accumulate(packed, pld, n, n, N.MODE_COUNT, want_dir=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ok, term, tot = mass_balance(dout[:, :n], acc[:, :n], 0, 1, n)
+    ms = sum(ms_dir) / len(ms_dir)
+    del t, packed, acc, dout
+    torch.cuda.empty_cache()
+    return {"workload": f"{n}x{n} fp32 fluvial terrain + N(0, {sigma} m) noise, rounded to cm (raw DEM)",
+            "pits": pits, "tie_cells": ties, "direction_ms": ms, "gcells_s": n * n / ms / 1e6,
+            "accumulation_ms": e0.elapsed_time(e1), "stats": info,
+            "algorithmic_bytes_per_cell": 5, "achieved": n * n * 5 / ms / 1e6, "peak": peak,
+            "unit": "GB/s", "frac": n * n * 5 / ms / 1e6 / peak,
+            "timing": "host wall clock around the synchronous entry point (its host loops read one "
+                      "device counter per round)",
+            "parity": {"acc_equals_one_plus_donors_everywhere": ok, "terminal_cells": term, "cells": tot}}
+
+
 def count_run(rank, world, rows, cols, peak, barrier, dev, steps=3):
     """D8 + cell-count accumulation on rows x cols per GPU (BASELINE.json configs[4] when
     8 x 12 500 x 100 000), checked by mass balance on every cell."""
@@ -596,6 +639,7 @@ def run_product(args):
                    "configs[3]": weighted_run(rank, world, 5000, 40000, peak, barrier, dev)}
     stencil = terrain_roofline(peak) if world == 1 else terrain_bands(peak, rank, world, barrier, dev)
     wfilter = window_filter_bench(peak) if world == 1 else None
+    general = general_path_run(peak, dev) if world == 1 else None
     if rank == 0:
         stencil["cpu_baseline"] = terrain_cpu_baseline(TERRAIN_N)
         g, dt = oracle_sample_gcells(2500, COLS, total_rows)
@@ -616,6 +660,7 @@ def run_product(args):
             "boundary_graph": {"resolve_rounds": resolve_rounds,
                                "note": "pointer-doubling rounds of stage B until no node is active"},
             "parity": parity, "weighted": weighted, "target_configs": targets,
+            "general_path": general,
             "stencil_roofline": stencil, "window_filter": wfilter,
             "cpu_baseline": cpu,
         }))

@@ -13,16 +13,29 @@ from hydrotools.cuda import watershed as W, _device as D, _native as N
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 dec = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 relief = float(sys.argv[3]) if len(sys.argv) > 3 else 800.0
+kind = sys.argv[4] if len(sys.argv) > 4 else "fbm"
 rng = np.random.default_rng(1)
-fy, fx = np.fft.fftfreq(n)[:, None], np.fft.fftfreq(n)[None, :]
-f = np.sqrt(fx * fx + fy * fy); f[0, 0] = 1
-z = np.fft.ifft2((rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))) / f ** 1.8).real
-dem = ((z - z.min()) / (z.max() - z.min()) * relief).round(dec).astype(np.float32)
-del z, f
 dev = D.require_cuda()
+if kind == "fbm":
+    # isotropic spectral noise: no drainage structure at all, a third of the cells in lakes
+    fy, fx = np.fft.fftfreq(n)[:, None], np.fft.fftfreq(n)[None, :]
+    f = np.sqrt(fx * fx + fy * fy); f[0, 0] = 1
+    z = np.fft.ifft2((rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))) / f ** 1.8).real
+    dem = ((z - z.min()) / (z.max() - z.min()) * relief).round(dec).astype(np.float32)
+    del z, f
+else:
+    # fluvial terrain (the bench's valley network) + measurement noise of `relief` metres s.d.,
+    # rounded to `dec` decimals: what a raw LiDAR / SRTM tile looks like -- many small pits, ties
+    from hydrotools.cuda import synth
+    t, tld = synth.synth_dem(20261019, n, n)
+    dem = t[:, :n].cpu().numpy()
+    del t
+    for r0 in range(0, n, 1000):
+        dem[r0:r0 + 1000] = (dem[r0:r0 + 1000] + rng.normal(0.0, relief, dem[r0:r0 + 1000].shape)
+                             ).round(dec).astype(np.float32)
 buf, ld = D.upload(dem, torch.float32, 4, dev)
 pits, ties = W._validate(buf, ld, n, n, None, dev)
-print(f"{n} x {n} raw fBm, {dec} decimals: {pits} pits, {ties} tie cells")
+print(f"{n} x {n} raw {kind}, {dec} decimals: {pits} pits, {ties} tie cells")
 for it in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     packed, pld, info = W.d8_general(buf, ld, n, n, None, 10.0, 10.0)
