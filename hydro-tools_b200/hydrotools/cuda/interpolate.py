@@ -96,7 +96,8 @@ def raster_filter(raster_source: str, kernel: Union[np.ndarray, tuple], method: 
     """Filter a raster using a defined kernel and method.
 
     Same signature as /root/reference/src/hydrotools/interpolate.py:110-117; the output
-    is float32 with NaN as nodata unless ``out_dtype`` is given."""
+    is float32 with the reference's float32 nodata (the type's minimum) unless ``out_dtype``
+    is given."""
     if args:
         raise NotImplementedError("percentile / quantile arguments are outside the CUDA path")
     a, meta = _io.read_raster(raster_source)
@@ -107,7 +108,9 @@ def raster_filter(raster_source: str, kernel: Union[np.ndarray, tuple], method: 
         filled = np.where(np.isnan(res), nd, res).astype(out_dtype)
         _io.write_raster(filled, raster_source, filter_dst, nodata=nd)
     else:
-        _io.write_raster(res, raster_source, filter_dst, nodata=float("nan"))
+        # to_raster fills masked cells with infer_nodata(float32) (raster.py:807-811)
+        nd = _io.infer_nodata("float32")
+        _io.write_raster(np.where(np.isnan(res), np.float32(nd), res), raster_source, filter_dst, nodata=nd)
 
 
 def custom_raster_filter(raster_source, kernel, func, filter_dst, *args, out_dtype=None):

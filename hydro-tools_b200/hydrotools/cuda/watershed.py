@@ -278,8 +278,9 @@ class FlowAccumulation:
     def contributing_area(self, dst: str):
         """Save the contributing area raster in km**2."""
         modals, meta = _io.read_raster(self.modals)
-        ca = (modals.astype(np.float64) * meta["csx"] * meta["csy"]) / 1e6
-        nd = float(np.finfo("float64").min)
+        # float32 like the reference (the modals raster is float32, watershed.py:341-355, 392-405)
+        ca = ((modals.astype(np.float64) * meta["csx"] * meta["csy"]) / 1e6).astype(np.float32)
+        nd = float(np.finfo("float32").min)
         ca[(ca == 0) | np.isnan(ca)] = nd
         _io.write_raster(ca, self.direction, dst, nodata=nd)
 
