@@ -28,7 +28,7 @@ namespace {
 constexpr int TW = 128, TH = 32, THREADS = 256;
 constexpr int MAXK = 33;  // largest kernel edge
 constexpr int CELLS = TW * TH / THREADS;
-enum { M_SUM = 0, M_MIN, M_MAX, M_DIFF, M_MEAN, M_STD, M_VAR, M_COUNT };
+enum { M_SUM = 0, M_MIN, M_MAX, M_DIFF, M_MEAN, M_STD, M_VAR, M_MEDIAN, M_MODE, M_COUNT };
 
 struct FilterArgs {
     int64_t rows, cols;
@@ -80,7 +80,118 @@ filter_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ F
             c[4 * i + j] = (p.hy0 + 4 * warp + i) * p.bw + p.hx0a + lane + 32 * j;
 
     float res[CELLS];
-    if (METHOD == M_MIN || METHOD == M_MAX || METHOD == M_DIFF) {
+    if (METHOD == M_MEDIAN) {
+        // np.nanmedian (interpolate.py:215-219): the middle value of the valid samples, the
+        // mean of the two middle ones (fp64) for an even count.  No sample is stored: the
+        // r-th smallest key is found bit by bit -- the largest v with #{key < v} <= r -- in 32
+        // counting passes over the window (keys = floats mapped to unsigned in their order).
+        auto key_of = [](float v) -> unsigned {
+            const unsigned b = __float_as_uint(v);
+            return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+        };
+        int n[CELLS];
+        unsigned pre[CELLS];
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            n[k] = 0;
+            pre[k] = 0u;
+        }
+        for (int o = 0; o < p.n_off; o++) {
+            const int d = p.off[o];
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                const float v = s[c[k] + d];
+                n[k] += v == v;
+            }
+        }
+        for (int bit = 31; bit >= 0; bit--) {
+            int cnt[CELLS];
+#pragma unroll
+            for (int k = 0; k < CELLS; k++)
+                cnt[k] = 0;
+            for (int o = 0; o < p.n_off; o++) {
+                const int d = p.off[o];
+#pragma unroll
+                for (int k = 0; k < CELLS; k++) {
+                    const float v = s[c[k] + d];
+                    cnt[k] += (v == v) && key_of(v) < (pre[k] | (1u << bit));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CELLS; k++)
+                if (n[k] && cnt[k] <= (n[k] - 1) / 2)
+                    pre[k] |= 1u << bit;
+        }
+        // pre = key of the lower middle value; the upper one is the same value if enough
+        // samples are <= it, else the smallest key above it
+        int le[CELLS];
+        unsigned nxt[CELLS];
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            le[k] = 0;
+            nxt[k] = 0xFFFFFFFFu;
+        }
+        for (int o = 0; o < p.n_off; o++) {
+            const int d = p.off[o];
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                const float v = s[c[k] + d];
+                if (v == v) {
+                    const unsigned q = key_of(v);
+                    le[k] += q <= pre[k];
+                    if (q > pre[k])
+                        nxt[k] = min(nxt[k], q);
+                }
+            }
+        }
+        auto val_of = [](unsigned q) -> float {
+            return __uint_as_float(q ^ ((q >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+        };
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            if (!n[k]) {
+                res[k] = __int_as_float(0x7fc00000);
+                continue;
+            }
+            const float lo = val_of(pre[k]);
+            const float hi = (n[k] & 1) || le[k] > n[k] / 2 ? lo : val_of(nxt[k]);
+            res[k] = (n[k] & 1) ? lo : (float)(((double)lo + (double)hi) * 0.5);
+        }
+    }
+    else if (METHOD == M_MODE) {
+        // the reference counts the values in a dictionary in scan order and keeps the first
+        // key whose count is strictly the largest (interpolate.py:174-201): the first value,
+        // in window scan order, of maximal multiplicity
+        int best[CELLS];
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            best[k] = 0;
+            res[k] = __int_as_float(0x7fc00000);
+        }
+        for (int o = 0; o < p.n_off; o++) {
+            const int d = p.off[o];
+            float cand[CELLS];
+            int cnt[CELLS];
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                cand[k] = s[c[k] + d];
+                cnt[k] = 0;
+            }
+            for (int o2 = 0; o2 < p.n_off; o2++) {
+                const int d2 = p.off[o2];
+#pragma unroll
+                for (int k = 0; k < CELLS; k++)
+                    cnt[k] += s[c[k] + d2] == cand[k]; // false for NaN
+            }
+#pragma unroll
+            for (int k = 0; k < CELLS; k++)
+                if (cnt[k] > best[k]) {
+                    best[k] = cnt[k];
+                    res[k] = cand[k];
+                }
+        }
+    }
+    else if (METHOD == M_MIN || METHOD == M_MAX || METHOD == M_DIFF) {
         float mn[CELLS], mx[CELLS];
 #pragma unroll
         for (int k = 0; k < CELLS; k++) {
@@ -315,7 +426,7 @@ int launch(const CUtensorMap &map, const FilterArgs &p, cudaStream_t st)
 } // namespace
 
 // kernel_host: kh x kw bytes in HOST memory (non-zero = cell selected), kh, kw <= 33.
-// method: 0 sum, 1 min, 2 max, 3 diff, 4 mean, 5 std, 6 variance.
+// method: 0 sum, 1 min, 2 max, 3 diff, 4 mean, 5 std, 6 variance, 7 median, 8 mode.
 // halo_top / halo_bot: valid rows of the neighbour bands directly above / below
 // `src` in the same allocation (0 = that side is the edge of the raster, NaN beyond).
 extern "C" int ht_window_filter_f32(const float *src, int64_t rows, int64_t cols, int64_t ld,
@@ -363,6 +474,8 @@ extern "C" int ht_window_filter_f32(const float *src, int64_t rows, int64_t cols
     case M_MEAN: return launch<M_MEAN>(map, p, st);
     case M_STD: return launch<M_STD>(map, p, st);
     case M_VAR: return launch<M_VAR>(map, p, st);
+    case M_MEDIAN: return launch<M_MEDIAN>(map, p, st);
+    case M_MODE: return launch<M_MODE>(map, p, st);
     }
     return HT_ERR_ARG;
 }

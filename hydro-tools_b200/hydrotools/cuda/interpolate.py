@@ -6,10 +6,10 @@ The reference runs a numba loop per dask chunk under
 ``da.map_overlap(depth, boundary=nan)``; here one sm_100a kernel
 (``ht_window_filter_f32``, csrc/ht_filter.cu) filters the raster with the tile +
 halo staged by TMA, NaN outside the raster.  Reducers: sum, min, max, diff, mean,
-std, variance.  ``mode``, ``median``, ``percentile`` and ``quantile`` (the last two
-cannot work in the reference either: its reducers call ``np.nanpercentile(sample)``
-without ``q``, interpolate.py:230-240) and custom numba callables raise
-``NotImplementedError`` -- there is no CPU fallback.
+std, variance, median, mode.  ``percentile`` and ``quantile`` (which cannot work in the
+reference either: its reducers call ``np.nanpercentile(sample)`` without ``q``,
+interpolate.py:230-240) and custom numba callables raise ``NotImplementedError`` -- there
+is no CPU fallback.
 """
 import ctypes as C
 from typing import Optional, Union
@@ -21,8 +21,9 @@ from . import _native as N
 from . import _device as D
 from . import _io
 
-METHODS = {"sum": 0, "min": 1, "max": 2, "diff": 3, "mean": 4, "std": 5, "variance": 6}
-_UNSUPPORTED = ("mode", "median", "percentile", "quantile")
+METHODS = {"sum": 0, "min": 1, "max": 2, "diff": 3, "mean": 4, "std": 5, "variance": 6, "median": 7,
+           "mode": 8}
+_UNSUPPORTED = ("percentile", "quantile")
 MAX_KERNEL = 33  # largest kernel edge the direct kernel stages (halo of 16 cells)
 RUNS_FROM = 64   # sum / mean with at least this many selected cells go through row prefix sums
 

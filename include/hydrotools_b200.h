@@ -252,7 +252,9 @@ int ht_basin_u8(const int8_t *fd, int64_t fd_ld, int64_t rows, int64_t cols, int
  * selected, kh, kw <= 33).  Window rows i - kh/2 .. i + kh - 1 - kh/2 (likewise columns),
  * NaN outside the raster; fp64 sample and reducer, fp32 result, NaN where the centre is
  * NaN (or equals `nodata`) or no selected cell holds data.
- * method: 0 sum, 1 min, 2 max, 3 diff (max - min), 4 mean, 5 std, 6 variance (ddof 0). */
+ * method: 0 sum, 1 min, 2 max, 3 diff (max - min), 4 mean, 5 std, 6 variance (ddof 0),
+ * 7 median (np.nanmedian), 8 mode (first value, in window scan order, of the largest
+ * multiplicity -- the reference's dictionary walk, interpolate.py:174-201). */
 int ht_window_filter_f32(const float *src, int64_t rows, int64_t cols, int64_t ld,
                          int has_nodata, float nodata, const unsigned char *kernel_host,
                          int kh, int kw, int method, float *out, int64_t out_ld,

@@ -20,7 +20,7 @@ restatement against them (and against the live reference when it is present).
 """
 import numpy as np
 
-METHODS = ("sum", "min", "max", "diff", "mean", "std", "variance")
+METHODS = ("sum", "min", "max", "diff", "mean", "std", "variance", "median", "mode")
 
 
 def window_geometry(kh, kw):
@@ -78,6 +78,18 @@ def raster_filter(a, kernel, method):
                         ss = ss + d * d
                     var = ss / np.maximum(n, 1)
                     r = var if method == "variance" else np.sqrt(var)
+        elif method == "median":
+            r = np.nanmedian(np.where(n[None] > 0, s, 0.0), axis=0)  # all-NaN windows are masked below
+        elif method == "mode":
+            # the reference's dictionary walk (interpolate.py:174-201): the first value, in
+            # sample order, whose multiplicity is strictly the largest
+            r = np.full((rows, cols), np.nan)
+            best = np.zeros((rows, cols), np.int64)
+            for layer in s:
+                cnt = (s == layer[None]).sum(0)  # NaN never equals
+                take = cnt > best
+                r = np.where(take, layer, r)
+                best = np.where(take, cnt, best)
         else:
             mn = np.where(np.isnan(s), np.inf, s).min(0)
             mx = np.where(np.isnan(s), -np.inf, s).max(0)

@@ -13,7 +13,7 @@ import pytest
 from oracle import rasterfilter as orf
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-METHODS = ["sum", "min", "max", "diff", "mean", "std", "variance"]
+METHODS = ["sum", "min", "max", "diff", "mean", "std", "variance", "median", "mode"]
 RTOL = 1e-6  # fp64 accumulation on both sides, float32 results
 
 
@@ -40,7 +40,9 @@ def test_restatement_matches_reference_goldens(fgold):
     for c in _cases(fgold):
         a, k = fgold[f"{c}__in"], fgold[f"{c}__kernel"]
         for m in METHODS:
-            _close(orf.raster_filter(a, k, m), fgold[f"{c}__{m}"], f"{c} {m}")
+            if f"{c}__{m}" in fgold:  # mode: the class rasters only (interpreted reference)
+                _close(orf.raster_filter(a, k, m), fgold[f"{c}__{m}"], f"{c} {m}")
+    assert "classes_disc3__mode" in fgold and "classes_4x5__median" in fgold
 
 
 def test_window_geometry():
@@ -78,7 +80,8 @@ def test_gpu_matches_reference_goldens(hc, fgold):
     for c in _cases(fgold):
         a, k = fgold[f"{c}__in"], fgold[f"{c}__kernel"]
         for m in METHODS:
-            _close(hc.window_filter(a, k, m), fgold[f"{c}__{m}"], f"{c} {m}")
+            if f"{c}__{m}" in fgold:
+                _close(hc.window_filter(a, k, m), fgold[f"{c}__{m}"], f"{c} {m}")
 
 
 @pytest.mark.gpu
@@ -97,8 +100,12 @@ def test_gpu_matches_restatement(hc, shape, kernel):
     elif kernel == "ring":
         kernel = np.ones((5, 5), bool)
         kernel[1:4, 1:4] = False
+    classes = np.round(a / 200.0)  # repeated values, so that mode and median ties mean something
     for m in METHODS:
-        _close(hc.window_filter(a, kernel, m), orf.raster_filter(a, kernel, m), f"{shape} {m}")
+        src = classes if m == "mode" else a
+        _close(hc.window_filter(src, kernel, m), orf.raster_filter(src, kernel, m), f"{shape} {m}")
+    _close(hc.window_filter(classes, kernel, "median"), orf.raster_filter(classes, kernel, "median"),
+           f"{shape} median of classes")
 
 
 @pytest.mark.gpu

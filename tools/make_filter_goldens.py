@@ -21,6 +21,18 @@ REF = "/root/reference/src/hydrotools/interpolate.py"
 sys.path.insert(0, ROOT)
 
 
+def _no_jit(*args, **kwargs):
+    if args and callable(args[0]):
+        return args[0]
+    return lambda f: f
+
+
+class _PyDict:
+    @staticmethod
+    def empty(key_type=None, value_type=None):
+        return {}
+
+
 def reference_functions():
     import numba
     src = open(REF).read()
@@ -37,12 +49,21 @@ def reference_functions():
         name = node.test.comparators[0].value
         fsrc = textwrap.dedent(ast.get_source_segment(src, node.body[0]))
         fns = {"np": np, "njit": numba.njit}
+        if name == "mode":
+            # `Dict.empty(key_type=np.float64, ...)` (interpolate.py:178-181) does not type with
+            # the numba of this image, so the reference's source of this one reducer -- and of
+            # apply_filter for it -- is executed as plain Python, with a dict (insertion-ordered
+            # like numba's typed Dict) standing in for `Dict.empty(...)`
+            fns = {"np": np, "njit": _no_jit, "Dict": _PyDict}
         try:
             exec(fsrc, fns)
             reducers[name] = fns["func"]
         except Exception:
-            pass  # mode needs numba.typed.Dict; not used here
+            pass
         node = node.orelse[0] if node.orelse and isinstance(node.orelse[0], ast.If) else None
+    py_ns = {"np": np, "njit": _no_jit}
+    exec(textwrap.dedent(apply_src), py_ns)
+    reducers["__py_apply_filter__"] = py_ns["apply_filter"]
     return ns["apply_filter"], reducers
 
 
@@ -73,7 +94,12 @@ def cases():
     a1[rng.random(a1.shape) < 0.1] = np.nan
     ring = disc(2)
     ring[2, 2] = False  # kernel without its centre
+    classes = rng.integers(0, 5, (41, 47)).astype(np.float32)  # repeated values: mode / median ties
+    classes[rng.random(classes.shape) < 0.15] = np.nan
     return {
+        "classes_3x3": (classes, (3, 3)),
+        "classes_4x5": (classes, (4, 5)),
+        "classes_disc3": (classes, disc(3)),
         "rand_3x3": (a1, (3, 3)),
         "rand_4x2": (a1, (4, 2)),          # even sizes: i_start != i_end
         "rand_1x5": (a1, (1, 5)),
@@ -86,14 +112,17 @@ def cases():
 
 def main():
     apply_filter, reducers = reference_functions()
-    methods = ["sum", "min", "max", "diff", "mean", "std", "variance"]
+    methods = ["sum", "min", "max", "diff", "mean", "std", "variance", "median", "mode"]
     out = {}
     for name, (a, kernel) in cases().items():
         out[f"{name}__in"] = a
         out[f"{name}__kernel"] = (np.ones(kernel, bool) if isinstance(kernel, tuple)
                                   else np.asarray(kernel, bool))
         for m in methods:
-            out[f"{name}__{m}"] = reference_filter(apply_filter, reducers[m], a, kernel)
+            if m == "mode" and not name.startswith("classes"):
+                continue  # interpreted: only the small class rasters
+            af = reducers["__py_apply_filter__"] if m == "mode" else apply_filter
+            out[f"{name}__{m}"] = reference_filter(af, reducers[m], a, kernel)
     dst = os.path.join(ROOT, "tests", "golden", "filter.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, f"({os.path.getsize(dst) / 1024:.0f} KiB, {len(out)} arrays)")
