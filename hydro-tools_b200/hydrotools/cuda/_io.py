@@ -203,6 +203,11 @@ def _fallback_write(a: np.ndarray, template: str, dst: str, nodata) -> None:
 # --------------------------------------------------------------------------
 # public boundary
 # --------------------------------------------------------------------------
+def os_environ_mode() -> str:
+    import os
+    return os.environ.get("HYDROTOOLS_CUDA_IO", "").lower()
+
+
 def infer_nodata(dtype) -> Union[float, int, bool]:
     """Nodata value the reference assigns to a data type
     (/root/reference/src/hydrotools/utils.py:242-265): the type's minimum for floats and
@@ -246,11 +251,33 @@ def same_grid(src_a: str, src_b: str, tolerance: float = 1e-6) -> bool:
             and ma["geo_tags"].get(34735) == mb["geo_tags"].get(34735))
 
 
-def write_raster(data: np.ndarray, template: str, destination: str, nodata=None,
+def device_io() -> bool:
+    """Write results with the device-side tile encoder (hydrotools.cuda._cog) instead of
+    ``hydrotools.raster.to_raster``?  Yes when the reference's I/O layer is not importable,
+    or when HYDROTOOLS_CUDA_IO=device asks for it."""
+    import os
+    mode = os.environ.get("HYDROTOOLS_CUDA_IO", "").lower()
+    if mode == "device":
+        return True
+    if mode in ("reference", "host"):
+        return False
+    return not HAVE_REFERENCE_IO
+
+
+def write_raster(data, template: str, destination: str, nodata=None,
                  as_cog: bool = True) -> None:
-    """Store a (rows, cols) array on the template's grid.  ``nodata`` cells must
-    already hold ``nodata``."""
-    if HAVE_REFERENCE_IO:
+    """Store a (rows, cols) array (numpy, or a CUDA tensor) on the template's grid.
+    ``nodata`` cells must already hold ``nodata``.  A CUDA tensor is compressed on the device
+    and written as a COG directly when device_io() says so; otherwise it is copied to the
+    host and goes the reference's way."""
+    import torch
+    if isinstance(data, torch.Tensor):
+        if data.is_cuda and device_io():
+            from . import _cog
+            _cog.write_cog(data, _read_ifd(template), destination, nodata=nodata, overviews=as_cog)
+            return
+        data = data.cpu().numpy()
+    if HAVE_REFERENCE_IO and os_environ_mode() != "device":
         import dask.array as da
         from hydrotools.config import CHUNKS  # type: ignore
         arr = da.from_array(data[None], chunks=CHUNKS)

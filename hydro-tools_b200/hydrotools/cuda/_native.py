@@ -79,6 +79,8 @@ SIGNATURES = {
     "ht_upstream_mean_f64": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _f64, _f64, _f64, _int, _i64,
                              _p, _i64, _p, C.c_size_t, C.POINTER(C.c_longlong), _p],
     "ht_basin_u8": [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, C.c_size_t, _p],
+    "ht_tiff_encode_tiles": [_p, _i64, _i64, _i64, _int, _u64, _p, C.c_size_t, _p, _p, _p, _p,
+                             C.c_size_t, _p],
     "ht_synth_dem_f32": [_p, _i64, _i64, _i64, _u64, _i64, _i64, _int, _f32, _p],
     "ht_synth_weight_f32": [_p, _i64, _i64, _i64, _u64, _i64, _p],
 }
@@ -96,6 +98,10 @@ lib.ht_acc_workspace_bytes.argtypes = [_i64, _i64]
 lib.ht_acc_workspace_bytes.restype = C.c_size_t
 lib.ht_acc_workspace_bytes_mode.argtypes = [_i64, _i64, _int]
 lib.ht_acc_workspace_bytes_mode.restype = C.c_size_t
+lib.ht_tiff_encode_bound.argtypes = [_i64, _i64, _int]
+lib.ht_tiff_encode_bound.restype = C.c_size_t
+lib.ht_tiff_encode_workspace_bytes.argtypes = [_i64, _i64, _int]
+lib.ht_tiff_encode_workspace_bytes.restype = C.c_size_t
 lib.ht_streams_workspace_bytes.argtypes = [_i64, _i64, _int, _i64]
 lib.ht_streams_workspace_bytes.restype = C.c_size_t
 lib.ht_d8_general_workspace_bytes.argtypes = [_i64, _i64]

@@ -184,8 +184,16 @@ def flow_direction_accumulation(
     if beautify:
         raise NotImplementedError("beautify (r.watershed -b) is outside the CUDA path")
     a, meta = _io.read_raster(dem)
-    fd, fa = flow_direction_accumulation_arrays(
-        a, nodata=meta["nodata"], csx=meta["csx"], csy=meta["csy"], positive_only=positive_only)
+    if _io.device_io():
+        # results stay in HBM: their 512 x 512 tiles are deflated there and only the
+        # compressed bytes cross PCIe (hydrotools.cuda._cog)
+        dev = D.require_cuda()
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        fd, fa = flow_direction_accumulation_arrays(
+            t, nodata=meta["nodata"], csx=meta["csx"], csy=meta["csy"], positive_only=positive_only)
+    else:
+        fd, fa = flow_direction_accumulation_arrays(
+            a, nodata=meta["nodata"], csx=meta["csx"], csy=meta["csy"], positive_only=positive_only)
     _io.write_raster(fd, dem, direction_grid, nodata=DIR_NODATA)
     _io.write_raster(fa, dem, accumulation_grid, nodata=float("nan"))
 

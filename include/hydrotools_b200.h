@@ -273,6 +273,24 @@ int ht_window_filter_runs_f32(const float *src, int64_t rows, int64_t cols, int6
                               int halo_top, int halo_bot, void *ws, size_t ws_bytes,
                               void *stream);
 
+/* ---- raster.to_raster, the on-disk step --------------------------
+ * replaces the compression half of  to_raster -> tiled 512 x 512 GeoTIFF -> gdal_translate COG
+ *   /root/reference/src/hydrotools/raster.py:794-846, utils.py:78-98, config.py:23-45
+ * A device raster (row pitch ld_bytes, samples of 1 / 2 / 4 / 8 bytes) becomes one zlib
+ * stream per 512 x 512 tile -- what TIFF compression 8 (deflate) stores -- so that only the
+ * compressed bytes cross PCIe; the host writes the BigTIFF / COG container
+ * (hydrotools/cuda/_cog.py).  pad_value: the sample stored beyond the raster edge inside
+ * edge tiles (little endian in the low bytes).  out: ht_tiff_encode_bound() bytes; tile t
+ * (row-major over the tile grid) is out[tile_off[t] .. + tile_size[t]), *total bytes in all.
+ * tile_off / tile_size / total are DEVICE memory; nothing synchronises. */
+size_t ht_tiff_encode_bound(int64_t rows, int64_t cols, int elem_bytes);
+size_t ht_tiff_encode_workspace_bytes(int64_t rows, int64_t cols, int elem_bytes);
+int ht_tiff_encode_tiles(const void *src, int64_t ld_bytes, int64_t rows, int64_t cols,
+                         int elem_bytes, unsigned long long pad_value, uint8_t *out,
+                         size_t out_cap, unsigned long long *tile_off,
+                         unsigned long long *tile_size, unsigned long long *total, void *ws,
+                         size_t ws_bytes, void *stream);
+
 /* ---- synthetic workloads (BASELINE.json configs 2-5) ----------------------
  * integer-exact fractal DEM / weights, see include/ht_synth.h */
 int ht_synth_dem_f32(float *dem, int64_t rows, int64_t cols, int64_t ld,

@@ -145,7 +145,7 @@ def test_gpu_nodata_value_and_device_tensors(hc):
 def test_gpu_limits_and_errors(hc):
     a = np.zeros((10, 10), np.float32)
     with pytest.raises(NotImplementedError):
-        hc.window_filter(a, (3, 3), "median")
+        hc.window_filter(a, (3, 3), "percentile")
     with pytest.raises(ValueError):
         hc.window_filter(a, (35, 3), "max")  # larger than the 33 x 33 the direct kernel stages
     with pytest.raises(IndexError):
