@@ -402,6 +402,43 @@ def general_path_run(peak, dev, n=10000, sigma=0.3, steps=3):
             "parity": {"acc_equals_one_plus_donors_everywhere": ok, "terminal_cells": term, "cells": tot}}
 
 
+def e2e_cog_run(host_dem, rows, cols, steps=3):
+    """The end-to-end step with the on-disk format produced on the device:
+    pinned host DEM -> H2D -> validate + D8 + accumulation -> 512 x 512 tiles of direction and
+    accumulation deflated in HBM -> D2H of the COMPRESSED tile streams (what to_raster would
+    have to compress on the host after 9 B/cell crossed PCIe).  Returns Gcells/s and the bytes
+    that travelled.  The container write itself (hydrotools.cuda._cog.write_cog) is a file
+    write of those bytes and is left out, like the reference's disk."""
+    import torch
+    import hydrotools.cuda as hc
+    from hydrotools.cuda import _cog
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sizes = {}
+
+    def step():
+        t = host_dem.to(dev, non_blocking=True)
+        fd, fa = hc.flow_direction_accumulation_arrays(t, nodata=None, csx=CSX, csy=CSY)
+        for name, a, pad in (("direction", fd, -128), ("accumulation", fa, float("nan"))):
+            data, off, size = _cog.encode_tiles(a, pad)
+            sizes[name] = int(len(data))
+        torch.cuda.synchronize()
+
+    step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    raw = rows * cols * 9
+    return {"value": rows * cols / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": rows * cols * 4, "d2h_bytes_per_step": sum(sizes.values()),
+            "compressed_bytes": sizes, "uncompressed_bytes": raw,
+            "compression_ratio": raw / max(sum(sizes.values()), 1),
+            "api": "flow_direction_accumulation_arrays (CUDA tensors) + _cog.encode_tiles: the compute and "
+                   "compression of hydrotools.cuda.flow_direction_accumulation(dem, fd.tif, fa.tif) with "
+                   "HYDROTOOLS_CUDA_IO=device, file write excluded"}
+
+
 def count_run(rank, world, rows, cols, peak, barrier, dev, steps=3):
     """D8 + cell-count accumulation on rows x cols per GPU (BASELINE.json configs[4] when
     8 x 12 500 x 100 000), checked by mass balance on every cell."""
@@ -559,6 +596,7 @@ def run_product(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    e2e_cog = e2e_cog_run(host_dem, rows, cols) if world == 1 else None
     # what the host link can do with exactly these buffers: H2D of the DEM and D2H of both
     # results at the same time (full duplex), every rank at once -- the floor of a step that
     # has to move 13 B/cell over PCIe
@@ -591,7 +629,7 @@ def run_product(args):
            "note": "bound by PCIe: 13 B/cell cross the host link every step",
            "hostlink_floor_ms": link * 1e3,
            "hostlink_gbs_aggregate": rows * cols * 13 * world / link / 1e9,
-           "frac_of_hostlink": link / dt, "numa": numa}
+           "frac_of_hostlink": link / dt, "numa": numa, "device_compressed": e2e_cog}
     # the e2e result must be the same answer
     fd_dev, fa_dev = engine.results()
     assert torch.equal(out_fd.to(dev), fd_dev) and torch.equal(out_fa.to(dev), fa_dev)

@@ -118,7 +118,7 @@ def write_cog(a: torch.Tensor, geo_tags: dict, dst: str, nodata=None, overviews:
     ifd_pos = []
     for e in all_entries:
         ifd_pos.append(pos)
-        pos += 8 + 20 * len(e) + 8
+        pos += (8 + 20 * len(e) + 8 + 7) // 8 * 8  # every IFD, value block and level 8-byte aligned
     extra_pos = []
     for e in all_entries:
         p = []
@@ -137,8 +137,12 @@ def write_cog(a: torch.Tensor, geo_tags: dict, dst: str, nodata=None, overviews:
         pos = (pos + 7) // 8 * 8
     with open(dst, "wb") as f:
         f.write(b"II" + struct.pack("<HHHQ", 43, 8, 0, ifd_pos[0]))
+        def pad_to(target):
+            assert f.tell() <= target
+            f.write(b"\x00" * (target - f.tell()))
+
         for k, e in enumerate(all_entries):
-            assert f.tell() == ifd_pos[k]
+            pad_to(ifd_pos[k])
             f.write(struct.pack("<Q", len(e)))
             for (tag, typ, cnt, b), xp in zip(e, extra_pos[k]):
                 if b is None:
@@ -154,12 +158,11 @@ def write_cog(a: torch.Tensor, geo_tags: dict, dst: str, nodata=None, overviews:
                     continue
                 if b is None:
                     b = struct.pack("<" + "Q" * cnt, *[int(o) + data_pos[k] for o in enc[k][1]])
-                assert f.tell() == xp
-                f.write(b + b"\x00" * (-len(b) % 8))
+                pad_to(xp)
+                f.write(b)
         for k in range(len(levels) - 1, -1, -1):
-            assert f.tell() == data_pos[k]
+            pad_to(data_pos[k])
             f.write(enc[k][0].tobytes())
-            f.write(b"\x00" * (-len(enc[k][0]) % 8))
         size = f.tell()
     return {"bytes": size, "compressed": int(sum(len(x[0]) for x in enc)),
             "raw": int(sum(lv.numel() * lv.element_size() for lv in levels)), "levels": len(levels)}
