@@ -10,11 +10,12 @@
 // per tile, which is what TIFF compression 8 (Adobe deflate) stores; the host writes the
 // BigTIFF / COG container around them (hydrotools/cuda/_cog.py).
 //
-// Encoder: a tile's byte stream is cut into 4 KiB chunks; ONE THREAD deflates one chunk --
+// Encoder: a tile's byte stream is cut into 4 KiB chunks; ONE WARP deflates one chunk --
 // greedy LZ77 (4-byte hash, matches inside the chunk) + the fixed Huffman code -- into a
 // private slot, byte-aligned by an empty stored block (the "sync flush" pigz uses to join
-// independently compressed pieces).  A warp stages its 32 chunks and hash tables in shared
-// memory, lane-interleaved so that lanes walking their own chunk hit different banks.  A
+// independently compressed pieces).  The lanes look at 32 consecutive positions per round
+// (match search in parallel, greedy parse by shuffles, codes placed by a prefix sum of their
+// bit lengths); chunk, hash table and output words live in shared memory, 16 warps per SM.  A
 // second kernel sizes the tiles, a third lays them out back to back with the zlib header
 // and the Adler-32 of the tile (combined from per-chunk sums).  Rasters are HBM-resident
 // row-major arrays of 1, 2, 4 or 8-byte samples; cells beyond the raster edge are padding.
@@ -25,9 +26,8 @@ namespace {
 constexpr int TILE = 512;
 constexpr int CHUNK = 4096;                // input bytes per thread
 constexpr int CW = CHUNK / 4;              // words
-constexpr int HASH_BITS = 9, HASH_SLOTS = 1 << HASH_BITS;
+constexpr int HASH_BITS = 11, HASH_SLOTS = 1 << HASH_BITS;
 constexpr int SLOT_WORDS = 1184;           // output slot: 4096 * 9 / 8 + header / flush, in words
-constexpr int WARP_SMEM = 32 * (CHUNK + HASH_SLOTS * 2); // 147456 B
 
 struct EncArgs {
     const uint8_t *src;
@@ -45,47 +45,21 @@ struct EncArgs {
 
 __device__ __forceinline__ uint32_t rev_bits(uint32_t v, int n) { return __brev(v) >> (32 - n); }
 
-struct BitWriter {
-    uint32_t *out;
-    unsigned long long buf;
-    int nbits, words;
-    __device__ __forceinline__ void put(uint32_t v, int n) // n <= 31
-    {
-        buf |= (unsigned long long)v << nbits;
-        nbits += n;
-        if (nbits >= 32) {
-            out[words++] = (uint32_t)buf;
-            buf >>= 32;
-            nbits -= 32;
-        }
-    }
-    __device__ __forceinline__ void align_byte()
-    {
-        const int r = nbits & 7;
-        if (r)
-            put(0u, 8 - r);
-    }
-    __device__ __forceinline__ int finish() // bytes written; the last partial word is stored too
-    {
-        const int bytes = words * 4 + (nbits + 7) / 8;
-        if (nbits)
-            out[words] = (uint32_t)buf;
-        return bytes;
-    }
-};
-
-// fixed Huffman code of RFC 1951 3.2.6, already bit-reversed for the LSB-first stream
-__device__ __forceinline__ void put_literal(BitWriter &w, uint32_t lit)
+// symbol of one parse position as (bits, nbits), nbits <= 31
+__device__ __forceinline__ void literal_code(uint32_t lit, uint32_t &bits, int &nbits)
 {
-    if (lit < 144)
-        w.put(rev_bits(0x30 + lit, 8), 8);
-    else
-        w.put(rev_bits(0x190 + (lit - 144), 9), 9);
+    if (lit < 144) {
+        bits = rev_bits(0x30 + lit, 8);
+        nbits = 8;
+    }
+    else {
+        bits = rev_bits(0x190 + (lit - 144), 9);
+        nbits = 9;
+    }
 }
 
-__device__ __forceinline__ void put_match(BitWriter &w, int len, int dist)
+__device__ __forceinline__ void match_code(int len, int dist, uint32_t &bits, int &nbits)
 {
-    // length symbol 257..285 + extra bits
     int sym, eb = 0, ev = 0;
     if (len == 258)
         sym = 285;
@@ -100,13 +74,16 @@ __device__ __forceinline__ void put_match(BitWriter &w, int len, int dist)
             ev = l & ((1 << eb) - 1);
         }
     }
-    if (sym < 280)
-        w.put(rev_bits(sym - 256, 7), 7);
-    else
-        w.put(rev_bits(0xC0 + (sym - 280), 8), 8);
-    if (eb)
-        w.put((uint32_t)ev, eb);
-    // distance symbol 0..29 (5 bits) + extra bits
+    if (sym < 280) {
+        bits = rev_bits(sym - 256, 7);
+        nbits = 7;
+    }
+    else {
+        bits = rev_bits(0xC0 + (sym - 280), 8);
+        nbits = 8;
+    }
+    bits |= (uint32_t)ev << nbits;
+    nbits += eb;
     int dsym, deb = 0, dev = 0;
     if (dist <= 4)
         dsym = dist - 1;
@@ -116,38 +93,55 @@ __device__ __forceinline__ void put_match(BitWriter &w, int len, int dist)
         dsym = 2 * k + ((m >> (k - 1)) & 1);
         dev = m & ((1 << deb) - 1);
     }
-    w.put(rev_bits(dsym, 5), 5);
-    if (deb)
-        w.put((uint32_t)dev, deb);
+    bits |= rev_bits(dsym, 5) << nbits;
+    nbits += 5;
+    bits |= (uint32_t)dev << nbits;
+    nbits += deb;
 }
 
-// one warp = 32 chunks; lane L's chunk word k lives at data[k * 32 + L]
-__global__ void __launch_bounds__(32)
+// ONE WARP deflates one chunk.  Per round the 32 lanes look at 32 consecutive positions:
+// hash lookup + match extension in parallel, a greedy parse of the round by shuffles (the
+// lane a match or literal ends on names the next parse position), then the selected lanes
+// write their codes at the bit offsets a warp prefix sum gives them (atomicOr into the
+// chunk's output words in shared memory) -- no lane ever walks the chunk alone.
+constexpr int WARPS = 4;
+constexpr int SM_DATA = CHUNK + 32;                    // chunk + zero padding for 4-byte reads
+constexpr int SM_TAB = HASH_SLOTS * 2;
+constexpr int SM_OUT = SLOT_WORDS * 4;
+constexpr int SM_WARP = SM_DATA + SM_TAB + SM_OUT;     // 12 992 B
+
+__global__ void __launch_bounds__(32 * WARPS)
 deflate_chunks_kernel(const EncArgs p, int64_t nchunks)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *data = reinterpret_cast<uint32_t *>(smem_raw);                       // [CW][32]
-    uint16_t *tab = reinterpret_cast<uint16_t *>(smem_raw + 32 * CHUNK);            // [HASH_SLOTS][32]
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *base = smem_raw + (size_t)warp * SM_WARP;
+    uint32_t *dataw = reinterpret_cast<uint32_t *>(base);
+    const uint8_t *data = base;
+    uint16_t *tab = reinterpret_cast<uint16_t *>(base + SM_DATA);
+    uint32_t *outw = reinterpret_cast<uint32_t *>(base + SM_DATA + SM_TAB);
     const int row_bytes = TILE * p.es;
     const bool aligned = !((uintptr_t)p.src & 3) && !(p.ld_bytes & 3);
-    for (int64_t c0 = (int64_t)blockIdx.x * 32; c0 < nchunks; c0 += (int64_t)gridDim.x * 32) {
-        // ---- stage: the warp copies chunk after chunk, 128 B per lane-row, transposing into
-        // the lane-interleaved layout
-        for (int l = 0; l < 32; l++) {
-            const int64_t c = c0 + l;
-            if (c >= nchunks)
-                break;
-            const int64_t tile = c / p.chunks_per_tile;
-            const int within = (int)(c - tile * p.chunks_per_tile);
-            const int64_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-            for (int k = lane; k < CW; k += 32) {
+    const unsigned full = 0xffffffffu;
+    auto load32 = [&](int i) -> uint32_t {
+        const int k = i >> 2, sh = (i & 3) * 8;
+        const uint32_t lo = dataw[k];
+        return sh ? __funnelshift_r(lo, dataw[k + 1], sh) : lo;
+    };
+    for (int64_t c = (int64_t)blockIdx.x * WARPS + warp; c < nchunks; c += (int64_t)gridDim.x * WARPS) {
+        // ---- stage the chunk (coalesced), clear table and output words
+        const int64_t tile = c / p.chunks_per_tile;
+        const int within = (int)(c - tile * p.chunks_per_tile);
+        const int64_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        unsigned long long s1 = 0, s2 = 0; // Adler-32 partial sums
+        for (int k = lane; k < CW + 8; k += 32) {
+            uint32_t word = 0;
+            if (k < CW) {
                 const int byte0 = 4 * k;
                 const int tr = within * p.rows_per_chunk + byte0 / row_bytes; // tile row
                 const int off = byte0 - (byte0 / row_bytes) * row_bytes;      // byte inside it
                 const int64_t r = ty * TILE + tr;
                 const int64_t gbyte = tx * (int64_t)row_bytes + off; // byte column in the raster row
-                uint32_t word = 0;
                 if (aligned && r < p.rows && gbyte + 4 <= p.cols * p.es)
                     word = *reinterpret_cast<const uint32_t *>(p.src + r * p.ld_bytes + gbyte);
                 else {
@@ -161,82 +155,160 @@ deflate_chunks_kernel(const EncArgs p, int64_t nchunks)
                         word |= v << (8 * b);
                     }
                 }
-                data[k * 32 + l] = word;
-            }
-        }
-        for (int k = 0; k < HASH_SLOTS; k++)
-            tab[k * 32 + lane] = 0;
-        __syncwarp();
-        const int64_t c = c0 + lane;
-        if (c < nchunks) {
-            auto word_at = [&](int k) -> uint32_t { return data[k * 32 + lane]; };
-            auto load32 = [&](int i) -> uint32_t { // 4 bytes at byte offset i (i + 4 <= CHUNK)
-                const int k = i >> 2, s = (i & 3) * 8;
-                const uint32_t lo = word_at(k), hi = s ? word_at(min(k + 1, CW - 1)) : 0u;
-                return s ? __funnelshift_r(lo, hi, s) : lo;
-            };
-            auto byte_at = [&](int i) -> uint32_t { return (word_at(i >> 2) >> ((i & 3) * 8)) & 0xFFu; };
-            // Adler-32 partial sums of the chunk
-            unsigned long long s1 = 0, s2 = 0;
-            for (int k = 0; k < CW; k++) {
-                const uint32_t wv = word_at(k);
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    const unsigned v = (wv >> (8 * b)) & 0xFFu;
+                    const unsigned v = (word >> (8 * b)) & 0xFFu;
                     s1 += v;
-                    s2 += (unsigned long long)(CHUNK - (4 * k + b)) * v;
+                    s2 += (unsigned long long)(CHUNK - (byte0 + b)) * v;
                 }
             }
-            p.chunk_s1[c] = s1;
-            p.chunk_s2[c] = s2;
-            const bool last = (c % p.chunks_per_tile) == p.chunks_per_tile - 1;
-            BitWriter w{p.slots + c * SLOT_WORDS, 0ull, 0, 0};
-            w.put(last ? 1u : 0u, 1); // BFINAL
-            w.put(1u, 2);             // BTYPE = 01: fixed Huffman
-            int pos = 0;
-            while (pos < CHUNK) {
-                int len = 0, dist = 0;
-                if (pos + 4 <= CHUNK) {
-                    const uint32_t v = load32(pos);
-                    const uint32_t h = (v * 2654435761u) >> (32 - HASH_BITS);
-                    const int cand = (int)tab[h * 32 + lane] - 1;
-                    tab[h * 32 + lane] = (uint16_t)(pos + 1);
-                    if (cand >= 0 && load32(cand) == v) {
-                        len = 4;
-                        const int lim = min(258, CHUNK - pos);
-                        while (len + 4 <= lim) {
-                            const uint32_t x = load32(pos + len) ^ load32(cand + len);
-                            if (x) {
-                                len += (__ffs(x) - 1) >> 3;
-                                break;
-                            }
-                            len += 4;
-                        }
-                        if (len + 4 > lim) // tail, byte by byte
-                            while (len < lim && byte_at(pos + len) == byte_at(cand + len))
-                                len++;
-                        dist = pos - cand;
+            dataw[k] = word;
+        }
+        for (int k = lane; k < HASH_SLOTS; k += 32)
+            tab[k] = 0xFFFF;
+        for (int k = lane; k < SLOT_WORDS; k += 32)
+            outw[k] = 0u;
+        __syncwarp();
+        const bool last = within == p.chunks_per_tile - 1;
+        // block header: BFINAL, BTYPE = 01 (fixed Huffman)
+        if (lane == 0)
+            outw[0] = (last ? 1u : 0u) | (1u << 1);
+        int bitpos = 3;
+        int next_free = 0; // first position not covered by a match yet
+        __syncwarp();
+        for (int rbase = 0; rbase < CHUNK; rbase += 32) {
+            const int pos = rbase + lane;
+            const uint32_t v = load32(pos);
+            const bool can = pos + 4 <= CHUNK;
+            const uint32_t h = (v * 2654435761u) >> (32 - HASH_BITS);
+            if (next_free >= rbase + 32) {
+                // the whole round lies inside a match already emitted: only remember the positions
+                if (can)
+                    tab[h] = (uint16_t)pos;
+                __syncwarp();
+                continue;
+            }
+            int len = 0, dist = 0;
+            int cand = -1;
+            if (can) {
+                const int t = tab[h];
+                if (t != 0xFFFF && load32(t) == v)
+                    cand = t;
+                else if (pos >= p.es && load32(pos - p.es) == v) // the previous sample: runs, periods
+                    cand = pos - p.es;
+                else if (pos >= 1 && load32(pos - 1) == v)
+                    cand = pos - 1;
+            }
+            __syncwarp();
+            if (can)
+                tab[h] = (uint16_t)pos; // after everybody has read: candidates come from earlier rounds
+            const int lim = min(258, CHUNK - pos);
+            if (cand >= 0) {
+                // enough to know whether the match leaves the round; the one match that does and
+                // is selected is extended to its full length below
+                len = 4;
+                const int cap = min(lim, 36);
+                while (len < cap) {
+                    const uint32_t x = load32(pos + len) ^ load32(cand + len);
+                    if (x) {
+                        len += (__ffs(x) - 1) >> 3;
+                        break;
                     }
+                    len += 4;
                 }
-                if (len >= 4) {
-                    put_match(w, len, dist);
-                    pos += len;
-                }
-                else {
-                    put_literal(w, byte_at(pos));
-                    pos++;
-                }
+                len = min(len, cap);
+                dist = pos - cand;
             }
-            w.put(0u, 7); // end of block (symbol 256)
-            if (!last) {  // empty stored block: byte-aligns the stream for the next chunk
-                w.put(0u, 3);
-                w.align_byte();
-                w.put(0x0000u, 16); // LEN
-                w.put(0xFFFFu, 16); // NLEN
+            // ---- greedy parse of the round: where does each position hand over?
+            int cur = max(next_free - rbase, 0);
+            unsigned sel;
+            if (__ballot_sync(full, len >= 4) == 0u) { // literals only
+                sel = full << cur;
+                cur = 32;
+            }
+            else {
+                const int jump = lane + (len >= 4 ? len : 1); // round-relative; >= 32 leaves the round
+                sel = 0u;
+                int lastsel = 0;
+                while (cur < 32) {
+                    sel |= 1u << cur;
+                    lastsel = cur;
+                    cur = __shfl_sync(full, jump, cur);
+                }
+                // the last selected position may hold a match cut at the cap: extend it
+                if (lane == lastsel && len >= 36 && len < lim) {
+                    while (len < lim) {
+                        const uint32_t x = load32(pos + len) ^ load32(cand + len);
+                        if (x) {
+                            len += (__ffs(x) - 1) >> 3;
+                            break;
+                        }
+                        len += 4;
+                    }
+                    len = min(len, lim);
+                }
+                cur = __shfl_sync(full, lane + (len >= 4 ? len : 1), lastsel);
+            }
+            next_free = rbase + cur;
+            // ---- codes of the selected positions at their bit offsets
+            const bool mine = (sel >> lane) & 1u;
+            uint32_t bits = 0;
+            int nbits = 0;
+            if (mine) {
+                if (len >= 4)
+                    match_code(len, dist, bits, nbits);
+                else
+                    literal_code(v & 0xFFu, bits, nbits);
+            }
+            int inc = nbits;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(full, inc, d);
+                if (lane >= d)
+                    inc += t;
+            }
+            const int total = __shfl_sync(full, inc, 31);
+            if (mine) {
+                const int at = bitpos + inc - nbits;
+                const int wd = at >> 5, sh = at & 31;
+                atomicOr(&outw[wd], bits << sh);
+                if (sh + nbits > 32)
+                    atomicOr(&outw[wd + 1], bits >> (32 - sh));
+            }
+            bitpos += total;
+            __syncwarp();
+        }
+        // ---- end of block; a non-final chunk ends on an empty stored block (byte alignment)
+        if (lane == 0) {
+            bitpos += 7; // symbol 256 = seven zero bits
+            if (!last) {
+                bitpos += 3;                       // BFINAL = 0, BTYPE = 00
+                bitpos = (bitpos + 7) & ~7;        // stored blocks start on a byte
+                const int at = bitpos + 16;        // LEN = 0x0000, then NLEN = 0xFFFF
+                const int wd = at >> 5, sh = at & 31;
+                outw[wd] |= 0xFFFFu << sh;
+                if (sh + 16 > 32)
+                    outw[wd + 1] |= 0xFFFFu >> (32 - sh);
+                bitpos += 32;
             }
             else
-                w.align_byte();
-            p.chunk_bytes[c] = (uint32_t)w.finish();
+                bitpos = (bitpos + 7) & ~7;
+            p.chunk_bytes[c] = (uint32_t)(bitpos >> 3);
+        }
+        bitpos = __shfl_sync(full, bitpos, 0);
+        __syncwarp();
+        uint32_t *slot = p.slots + c * SLOT_WORDS;
+        for (int k = lane; k < (bitpos + 31) >> 5; k += 32)
+            slot[k] = outw[k];
+        // Adler-32 sums of the chunk
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            s1 += __shfl_down_sync(full, s1, d);
+            s2 += __shfl_down_sync(full, s2, d);
+        }
+        if (lane == 0) {
+            p.chunk_s1[c] = s1;
+            p.chunk_s2[c] = s2;
         }
         __syncwarp();
     }
@@ -381,10 +453,9 @@ extern "C" int ht_tiff_encode_tiles(const void *src, int64_t ld_bytes, int64_t r
     p.chunk_s1 = (unsigned long long *)b; b += align_up((size_t)nchunks * 8);
     p.chunk_s2 = (unsigned long long *)b;
     HT_CUDA_TRY(cudaFuncSetAttribute(deflate_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     WARP_SMEM));
-    const int64_t warps = (nchunks + 31) / 32;
-    const int grid = (int)std::min<int64_t>(warps, (int64_t)ht::kSMs * 16);
-    deflate_chunks_kernel<<<grid, 32, WARP_SMEM, st>>>(p, nchunks);
+                                     WARPS * SM_WARP));
+    const int grid = (int)std::min<int64_t>((nchunks + WARPS - 1) / WARPS, (int64_t)ht::kSMs * 4 * 8);
+    deflate_chunks_kernel<<<grid, 32 * WARPS, WARPS * SM_WARP, st>>>(p, nchunks);
     HT_LAUNCH_CHECK();
     tile_sizes_kernel<<<ht::cdiv(ntiles, 128), 128, 0, st>>>(p.chunk_bytes, p.chunks_per_tile, ntiles, tile_size);
     tile_offsets_kernel<<<1, 1024, 0, st>>>(tile_size, ntiles, tile_off, total);

@@ -31,9 +31,15 @@ _GEO_TAGS = (33550, 33922, 34264, 34735, 34736, 34737)
 _TYPE_FMT = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 8: "h", 9: "i", 11: "f", 12: "d", 16: "Q", 17: "q"}
 
 
-def encode_tiles(a: torch.Tensor, pad=0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+_STAGE = {}
+
+
+def encode_tiles(a: torch.Tensor, pad=0, copy: bool = True) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Deflate the 512 x 512 tiles of a 2-D CUDA tensor.  Returns (bytes uint8 [total],
-    tile offsets into it, tile sizes), tiles row-major over the tile grid, each a zlib stream."""
+    tile offsets into it, tile sizes), tiles row-major over the tile grid, each a zlib stream.
+    ``copy=False`` returns a view of a reusable page-locked staging buffer (valid until the
+    next call with the same ``stage`` key): the compressed bytes are copied once, device ->
+    pinned host, and written to the file from there."""
     if a.dim() != 2 or not a.is_cuda:
         raise ValueError("expected a 2-D CUDA tensor")
     if a.stride(1) != 1:
@@ -54,7 +60,15 @@ def encode_tiles(a: torch.Tensor, pad=0) -> Tuple[np.ndarray, np.ndarray, np.nda
            meta.data_ptr() + 16 * ntiles, ws.data_ptr(), ws.numel(), D.stream_ptr())
     m = meta.cpu().numpy()  # synchronises
     total = int(m[2 * ntiles])
-    return D.download(out[:total]), m[:ntiles].copy(), m[ntiles:2 * ntiles].copy()
+    key = (a.dtype, rows >= cols)
+    stage = _STAGE.get(key)
+    if stage is None or stage.numel() < total:
+        stage = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _STAGE[key] = stage
+    stage[:total].copy_(out[:total], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    host = stage[:total].numpy()
+    return (host.copy() if copy else host), m[:ntiles].copy(), m[ntiles:2 * ntiles].copy()
 
 
 def _np_dtype(dt: torch.dtype):
@@ -77,7 +91,7 @@ def write_cog(a: torch.Tensor, geo_tags: dict, dst: str, nodata=None, overviews:
     np_dt = np.dtype(_np_dtype(a.dtype))
     levels = overview_levels(a) if overviews else [a]
     pad = 0 if nodata is None or (isinstance(nodata, float) and np.isnan(nodata) and np_dt.kind != "f") else nodata
-    enc = [encode_tiles(lv, pad) for lv in levels]
+    enc = [encode_tiles(lv, pad) for lv in levels]  # copies: the levels share one staging buffer
 
     def entries_for(k, lv):
         h, w = int(lv.shape[0]), int(lv.shape[1])
