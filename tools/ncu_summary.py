@@ -36,12 +36,20 @@ METRICS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu.sum",
     "lts__t_sector_hit_rate.pct",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "smsp__inst_executed_op_shared_atom.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum",
 ]
 
 # bench.py's stage names for the kernels of the path
 BENCH_NAME = [
     (r"d8_kernel", "d8_kernel"),
     (r"acc_fused", "acc_fused_kernel"),
+    (r"acc_local_w", "acc_local_w_kernel"),
+    (r"acc_final_w", "acc_final_w_kernel"),
+    (r"coarse_resolve_kernel<.*i128", "coarse_resolve_kernel<i128>"),
+    (r"weight_max", "weight_max_kernel"),
     (r"acc_local", "acc_local_cnt_kernel"),
     (r"coarse_resolve", "coarse_resolve_kernel"),
     (r"acc_final", "acc_final_cnt_kernel"),
