@@ -412,6 +412,62 @@ run_filter_kernel(const float *src, int64_t ld, int64_t rows, int64_t cols, int 
     }
 }
 
+// The same sums with the prefix rows of one output tile staged in shared memory: every P / Cn
+// entry is read from L2 once per tile instead of once per kernel row that touches it (a disc
+// of radius 10 reads each entry ~20 times), and the clamping of the run ends to the raster is
+// done while staging.  Tile = th rows x 128 columns; staged block = (th + kh - 1) x (128 + kw)
+// entries of 12 B.  Used when that fits shared memory; larger kernels keep the kernel above.
+__global__ void __launch_bounds__(256)
+run_filter_tiled_kernel(const float *src, int64_t ld, int64_t rows, int64_t cols, int halo_top,
+                        int halo_bot, int has_nodata, float nodata, const double *P, const unsigned *Cn,
+                        int64_t pld, const Run *runs, int n_runs, int i_start, int j_start, int mean,
+                        float *out, int64_t out_ld, int th, int R, int C)
+{
+    extern __shared__ __align__(16) unsigned char fsm[];
+    double *sP = reinterpret_cast<double *>(fsm);
+    unsigned *sC = reinterpret_cast<unsigned *>(fsm + (size_t)R * C * 8);
+    Run *srun = reinterpret_cast<Run *>(fsm + (size_t)R * C * 12);
+    const int64_t x0 = (int64_t)blockIdx.x * 128, y0 = (int64_t)blockIdx.y * th;
+    for (int i = threadIdx.x; i < n_runs; i += 256)
+        srun[i] = runs[i];
+    for (int idx = threadIdx.x; idx < R * C; idx += 256) {
+        const int rr = idx / C, cc = idx - rr * C;
+        const int64_t yy = y0 - i_start + rr;
+        double pv = 0.0;
+        unsigned cv = 0u;
+        if (yy >= -(int64_t)halo_top && yy < rows + halo_bot) {
+            const int64_t X = min(max(x0 - j_start + cc, (int64_t)0), cols);
+            const int64_t at = (yy + halo_top) * pld + X;
+            pv = P[at];
+            cv = Cn[at];
+        }
+        sP[idx] = pv;
+        sC[idx] = cv;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 127;
+    const int64_t x = x0 + lx;
+    if (x >= cols)
+        return;
+    const int half = th / 2, ly0 = (threadIdx.x >> 7) * half;
+    for (int ly = ly0; ly < ly0 + half; ly++) {
+        const int64_t y = y0 + ly;
+        if (y >= rows)
+            break;
+        double sum = 0.0;
+        unsigned n = 0u;
+        for (int r = 0; r < n_runs; r++) {
+            const Run q = srun[r];
+            const int at = (ly + q.ky) * C + lx;
+            sum += sP[at + q.b + 1] - sP[at + q.a];
+            n += sC[at + q.b + 1] - sC[at + q.a];
+        }
+        const float centre = src[y * ld + x];
+        const bool ok = centre == centre && !(has_nodata && centre == nodata) && n;
+        out[y * out_ld + x] = ok ? (float)(mean ? sum / (double)n : sum) : __int_as_float(0x7fc00000);
+    }
+}
+
 template <int METHOD>
 int launch(const CUtensorMap &map, const FilterArgs &p, cudaStream_t st)
 {
@@ -549,6 +605,22 @@ extern "C" int ht_window_filter_runs_f32(const float *src, int64_t rows, int64_t
         base, ld, rows_all, cols, has_nodata && nodata == nodata, nodata, P, Cn, pld);
     HT_LAUNCH_CHECK();
     const int i_start = kh / 2, j_start = kw / 2;
+    // tile rows: the largest of 32 / 16 / 8 whose staged prefix block fits (two CTAs per SM if possible)
+    for (int th = 32; th >= 8; th >>= 1) {
+        const int R = th + kh - 1, C = 128 + kw;
+        const size_t need = (size_t)R * C * 12 + (size_t)n_runs * sizeof(Run) + 16;
+        if (need > (th == 32 ? 110u : 200u) * 1024u)
+            continue;
+        HT_CUDA_TRY(cudaFuncSetAttribute(run_filter_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)need));
+        dim3 tgrid((unsigned)ht::cdiv(cols, 128), (unsigned)ht::cdiv(rows, th));
+        run_filter_tiled_kernel<<<tgrid, 256, need, st>>>(src, ld, rows, cols, halo_top, halo_bot,
+                                                          has_nodata && nodata == nodata, nodata, P, Cn, pld,
+                                                          druns, n_runs, i_start, j_start, method == M_MEAN,
+                                                          out, out_ld, th, R, C);
+        HT_LAUNCH_CHECK();
+        return HT_OK;
+    }
     const size_t smem = (size_t)n_runs * sizeof(Run);
     if (smem > 48 * 1024)
         HT_CUDA_TRY(cudaFuncSetAttribute(run_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
