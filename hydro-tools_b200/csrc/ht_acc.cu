@@ -164,10 +164,10 @@ constexpr unsigned FLAGS_STOP = HT_DIR_NEG | HT_DIR_EDGE | HT_DIR_NULL;
 constexpr unsigned J_PTR = 0x1FFEu, J_ACTIVE = 1u;
 constexpr int MAX_ROUNDS = 13; // 2^13 > T*T: only a cyclic (invalid) direction grid gets here
 
-constexpr int SMC_PTR = SM_EFF;                  // uint16[T*T] pointer entries
-constexpr int SMC_ARR = SMC_PTR + T * T * 2;     // uint32[T*T] sums that arrived at a cell
-constexpr int SMC_LUT = SMC_ARR + T * T * 4;     // uint32[16] code -> pointer step | active
-constexpr int SMC_BAR = SMC_LUT + 64;            // mbarrier, then counters
+constexpr int SMC_PTR = SM_EFF;                  // uint32[T*T] pointer entries
+constexpr int SMC_ARR = SMC_PTR + T * T * 4;     // uint32[T*T] own value + sums that arrived at a cell
+constexpr int SMC_LUT = SMC_ARR + T * T * 4;     // uint32[2][16] code -> pointer step | active (as stored, transposed)
+constexpr int SMC_BAR = SMC_LUT + 128;           // mbarrier, then counters
 constexpr int SMC_TOTAL = SMC_BAR + 32;
 
 // offset (dr * T + dc) of GRASS code 1..8 inside the T x T tile arrays
@@ -211,19 +211,64 @@ __device__ __forceinline__ bool leaves_tile(unsigned b, int ly, int lx, int th, 
     return !(b & FLAGS_STOP) && ((ex >> (b & HT_DIR_CODE)) & 1u);
 }
 
+// Orientation.  Lanes of a warp own 32 consecutive cells of one row of the tile arrays;
+// their hand-offs of round k land 2^k steps downstream.  Flow lines that run ACROSS the
+// warp's row coalesce (neighbouring lines merge at every confluence), so after a few rounds
+// most lanes of the warp target the same trunk cells and the shared atomics serialise
+// (6 wavefronts per ATOMS on the benchmark DEM, whose rivers run north-south; 2 when the
+// warp lies along the flow); cells ALONG one flow line hand on to distinct cells in every
+// round.  So every tile first votes on its dominant flow axis (two-step displacements of
+// sampled cells) and, when it is the row axis, keeps its arrays TRANSPOSED: array index =
+// lx * T + ly.  Pointers are array addresses, so the rounds do not know about it.
+__device__ __forceinline__ int arr_index(bool tr, int ly, int lx) { return tr ? lx * T + ly : ly * T + lx; }
+
+// The rounds are written branch-free in PTX on 32-bit shared addresses: a pointer entry IS
+// the shared address of the target's entry (| active bit), its arrival word sits CNT_DELTA
+// bytes behind.  No generic-address arithmetic, no divergent regions: the 16 hand-offs of a
+// thread issue back to back and their latencies overlap.
+constexpr int CNT_DELTA = T * T * 4;
+// round, first half: active -> add `a` to the arrivals of the target, fetch the target's entry
+__device__ __forceinline__ void cnt_hand_on(unsigned &low, unsigned a)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, f;\n"
+        "and.b32 f, %0, 1;\n"
+        "setp.ne.u32 p, f, 0;\n"
+        "and.b32 t, %0, 0xFFFFFFFC;\n"
+        "@p red.shared.add.u32 [t + %2], %1;\n"
+        "@p ld.shared.u32 %0, [t];\n"
+        "}\n"
+        : "+r"(low)
+        : "r"(a), "n"(CNT_DELTA)
+        : "memory");
+}
+// round, second half: publish the new entry, snapshot the own arrivals
+__device__ __forceinline__ unsigned cnt_publish(unsigned own_addr, unsigned low)
+{
+    unsigned a;
+    asm volatile(
+        "st.shared.u32 [%1], %2;\n"
+        "ld.shared.u32 %0, [%1 + %3];\n"
+        : "=r"(a)
+        : "r"(own_addr), "r"(low), "n"(CNT_DELTA)
+        : "memory");
+    return a;
+}
+
 template <int WMODE>
 __global__ void __launch_bounds__(THREADS, 4)
 acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *pk = smem_raw;
-    unsigned char *ptrb = smem_raw + SMC_PTR;   // uint16[T*T]
-    unsigned char *arrb = smem_raw + SMC_ARR;   // uint32[T*T]
-    uint16_t *ptr16 = reinterpret_cast<uint16_t *>(ptrb);
-    uint32_t *arr = reinterpret_cast<uint32_t *>(arrb);
-    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMC_LUT);
+    uint32_t *ptr32 = reinterpret_cast<uint32_t *>(smem_raw + SMC_PTR); // entries
+    uint32_t *arr = reinterpret_cast<uint32_t *>(smem_raw + SMC_ARR);   // own value + arrivals
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMC_LUT);   // [0..15] as stored, [16..31] transposed
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMC_BAR);
-    int *ctl = reinterpret_cast<int *>(smem_raw + SMC_BAR + 8); // [0] entries of the tile, [1] their place in the list
+    int *ctl = reinterpret_cast<int *>(smem_raw + SMC_BAR + 8); // [0] entries of the tile, [1] their place in the list, [2] orientation vote
+    static_assert(SMC_ARR - SMC_PTR == CNT_DELTA, "arrival word = entry + CNT_DELTA");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -231,77 +276,92 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
     if (tid == 0) {
         ctl[0] = 0;
+        ctl[2] = 0;
         ht::mbar_init(&bar, 1);
         ht::fence_mbar_init();
         ht::mbar_expect_tx(&bar, RH * RP);
         ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
     }
-    if (tid < 16) // added to 2 * (cell index); codes 0, 9..15 never link
-        lut[tid] = link_offset_of(tid) ? (unsigned)(link_offset_of(tid) * 2) + J_ACTIVE : 0u;
+    if (tid < 32) { // added to the own entry address; codes 0, 9..15 never link
+        const int code = tid & 15;
+        const int off = tid < 16 ? link_offset_of(code) : code_dc(code) * T + code_dr(code);
+        lut[tid] = link_offset_of(code) ? (unsigned)(off * 4) + J_ACTIVE : 0u;
+    }
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
-    // thread -> cells tid + 256 k: one column, every 4th row.  A warp covers 32
-    // consecutive cells of a row in every step (conflict-free own accesses).
-    const int lx = tid & (T - 1), ly0 = tid >> 6;
-#pragma unroll
-    for (int k = 0; k < CPT; k++)
-        arr[tid + k * THREADS] = 0u;
+    // thread -> array cells tid + 256 k: one array column u, every 4th array row.  A warp
+    // covers 32 consecutive array cells in every step (conflict-free own accesses).
+    const int u = tid & (T - 1), v0 = tid >> 6;
+    const unsigned pbase = ht::smem_u32(ptr32), own0 = pbase + 4u * (unsigned)tid;
     __syncthreads();
     ht::mbar_wait(&bar, 0);
 
-    // ---- per cell: low = pointer entry, a = sum to hand on, own = the cell's own value
-    unsigned low[CPT], a[CPT];
-    unsigned own = 0; // bit k: own value of cell k
+    // ---- orientation vote: 4 sampled cells per thread, displacement over two steps
     {
-        // codes that do not link from this column; bit 15: outside the raster; bit 0: code 0
-        const unsigned cm = (lx == 0 ? EX_W : 0u) | (lx == tw - 1 ? EX_E : 0u) | (lx >= tw ? 0xFFFFu : 0u) | 1u;
+        int score = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int at = (v0 + 16 * j + 1) * RP + XO + u;
+            const unsigned b = pk[at];
+            const int c1 = (int)(b & HT_DIR_CODE);
+            if (!(b & FLAGS_STOP) && c1) {
+                int ddr = code_dr(c1), ddc = code_dc(c1);
+                const unsigned b2 = pk[at + ddr * RP + ddc];
+                const int c2 = (int)(b2 & HT_DIR_CODE);
+                if (!(b2 & FLAGS_STOP) && c2) {
+                    ddr += code_dr(c2);
+                    ddc += code_dc(c2);
+                }
+                score += (abs(ddr) > abs(ddc)) - (abs(ddr) < abs(ddc));
+            }
+        }
+        score = __reduce_add_sync(0xffffffffu, score);
+        if (lane == 0 && score)
+            atomicAdd(&ctl[2], score);
+    }
+    __syncthreads();
+    const bool tr = ctl[2] > 0; // flow runs along the raster's columns: keep the arrays transposed
+    const uint32_t *lutm = lut + (tr ? 16 : 0);
+
+    // ---- per cell: low = pointer entry, a = sum to hand on (own value + arrivals so far)
+    unsigned low[CPT], a[CPT];
+    {
+        // u is the raster column (as stored) or the raster row (transposed)
+        const int lim_u = tr ? th : tw, lim_v = tr ? tw : th;
+        const unsigned lo_u = tr ? EX_N : EX_W, hi_u = tr ? EX_S : EX_E;
+        const unsigned lo_v = tr ? EX_W : EX_N, hi_v = tr ? EX_E : EX_S;
+        // codes that do not link from this array column; bit 15: outside the raster; bit 0: code 0
+        const unsigned cm = (u == 0 ? lo_u : 0u) | (u == lim_u - 1 ? hi_u : 0u) | (u >= lim_u ? 0xFFFFu : 0u) | 1u;
+        const int pk0 = tr ? (u + 1) * RP + XO + v0 : (v0 + 1) * RP + XO + u, pks = tr ? 4 : 4 * RP;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            const int ly = ly0 + 4 * k;
-            const unsigned b = pk[(ly + 1) * RP + XO + lx];
-            const unsigned ex = cm | (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u) | (ly >= th ? 0xFFFFu : 0u);
+            const int v = v0 + 4 * k;
+            const unsigned b = pk[pk0 + k * pks];
+            const unsigned ex = cm | (v == 0 ? lo_v : 0u) | (v == lim_v - 1 ? hi_v : 0u) | (v >= lim_v ? 0xFFFFu : 0u);
             const unsigned code = b & HT_DIR_CODE;
             // no link: a stop flag, or the receiver is outside the tile / the raster
             const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
             const bool valid = !(b & HT_DIR_NULL) && !(ex >> 15);
-            const unsigned val = WMODE == W_ONE ? (valid ? 1u : 0u) : ((valid && (b & HT_DIR_TAINT)) ? 1u : 0u);
-            own |= val << k;
-            a[k] = val;
-            low[k] = 2u * (unsigned)(tid + k * THREADS) + (stop ? 0u : lut[code]);
-            ptr16[tid + k * THREADS] = (uint16_t)low[k];
+            a[k] = WMODE == W_ONE ? (valid ? 1u : 0u) : ((valid && (b & HT_DIR_TAINT)) ? 1u : 0u);
+            low[k] = own0 + (unsigned)(k * THREADS * 4) + (stop ? 0u : lutm[code]);
+            ptr32[tid + k * THREADS] = low[k];
+            arr[tid + k * THREADS] = a[k];
         }
     }
     __syncthreads();
 
-    // ---- pointer doubling.  Only the pointer entries live in shared memory (they are
-    // what other cells read); sums arrive in arr[] and are snapshot into registers.
+    // ---- pointer doubling
     for (int round = 0; round < MAX_ROUNDS; round++) {
-        unsigned was = 0; // cells that were active in this round
 #pragma unroll
-        for (int k = 0; k < CPT; k++) {
-            if (low[k] & J_ACTIVE) {
-                const unsigned t2 = low[k] & J_PTR; // 2 * (cell 2^k steps downstream)
-                const unsigned wt = *reinterpret_cast<const uint16_t *>(ptrb + t2);
-                if (WMODE == W_ONE || a[k])
-                    atomicAdd(reinterpret_cast<uint32_t *>(arrb + 2 * t2), a[k]);
-                // t still active: its pointer is 2^(k+1) steps from me; else I am done and
-                // keep the root of the path (t's pointer; a root points at itself)
-                low[k] = wt;
-                was |= 1u << k;
-            }
-        }
+        for (int k = 0; k < CPT; k++)
+            cnt_hand_on(low[k], a[k]);
         __syncthreads();
-        bool still = false;
+        unsigned any = 0;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            if ((was >> k) & 1u) {
-                ptr16[tid + k * THREADS] = (uint16_t)low[k];
-                if (low[k] & J_ACTIVE) {
-                    a[k] = ((own >> k) & 1u) + arr[tid + k * THREADS];
-                    still = true;
-                }
-            }
+            a[k] = cnt_publish(own0 + (unsigned)(k * THREADS * 4), low[k]);
+            any |= low[k];
         }
-        if (!__syncthreads_or(still))
+        if (!__syncthreads_or((int)(any & J_ACTIVE)))
             break;
     }
 
@@ -312,8 +372,7 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         const unsigned b = per ? pk[(ly + 1) * RP + plx + XO] : (unsigned)HT_DIR_NULL;
         // flow that leaves the tile through this cell
         if (per && leaves_tile(b, ly, plx, th, tw)) {
-            const unsigned self = WMODE == W_ONE ? 1u : ((b & HT_DIR_TAINT) ? 1u : 0u);
-            const unsigned val = self + arr[ly * T + plx];
+            const unsigned val = arr[arr_index(tr, ly, plx)];
             if (val)
                 atomicAdd(reinterpret_cast<unsigned long long *>(p.base) +
                               exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE)),
@@ -330,8 +389,8 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                 const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
                 if (ny >= 1 && ny <= th && nx >= XO && nx < XO + tw)
                     continue; // inside the tile
-                const unsigned u = pk[ny * RP + nx]; // outside the raster: TMA filled 0
-                entry |= !(u & FLAGS_STOP) && (u & HT_DIR_CODE) == (unsigned)win2code(8 - kk);
+                const unsigned w = pk[ny * RP + nx]; // outside the raster: TMA filled 0
+                entry |= !(w & FLAGS_STOP) && (w & HT_DIR_CODE) == (unsigned)win2code(8 - kk);
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, entry);
@@ -345,7 +404,8 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         __syncthreads();
         if (entry) {
             // where the path that enters here leaves the tile: the root of the cell
-            const int rc = (int)(ptr16[ly * T + plx] >> 1), cy = rc >> 6, cx = rc & (T - 1);
+            const int rc = (int)(((ptr32[arr_index(tr, ly, plx)] & ~3u) - pbase) >> 2);
+            const int cy = tr ? (rc & (T - 1)) : (rc >> 6), cx = tr ? (rc >> 6) : (rc & (T - 1));
             const unsigned rb = pk[(cy + 1) * RP + cx + XO];
             const int32_t slot = tile * SLOTS + tid;
             p.list[ctl[1] + at] = slot;
@@ -355,14 +415,28 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         }
     }
 
-    // ---- tile-local counts for stage C (u16; a warp stores 64 consecutive bytes)
-    if (lx < tw) {
-        uint16_t *dst = p.lacc + (y0 + ly0) * p.lacc_ld + x0 + lx;
+    // ---- tile-local counts for stage C (u16; a warp stores 64 consecutive bytes).
+    // a[] holds them: the last snapshot was taken after the last hand-off.
+    if (tr) {
+        // transposed arrays: turn them through a padded u16 buffer (33-word pitch: both the
+        // column-wise writes and the row-wise reads are conflict-free) laid over the entries
+        __syncthreads();
+        uint16_t *buf = reinterpret_cast<uint16_t *>(ptr32);
+#pragma unroll
+        for (int k = 0; k < CPT; k++)
+            buf[u * (T + 2) + v0 + 4 * k] = (uint16_t)a[k]; // (ly = u, lx = v)
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CPT; k++)
+            a[k] = buf[(v0 + 4 * k) * (T + 2) + u];
+    }
+    if (u < tw) {
+        uint16_t *dst = p.lacc + (y0 + v0) * p.lacc_ld + x0 + u;
         const int64_t step = 4 * p.lacc_ld;
 #pragma unroll
         for (int k = 0; k < CPT; k++, dst += step)
-            if (ly0 + 4 * k < th)
-                *dst = (uint16_t)(((own >> k) & 1u) + arr[tid + k * THREADS]);
+            if (v0 + 4 * k < th)
+                *dst = (uint16_t)a[k];
     }
 }
 
