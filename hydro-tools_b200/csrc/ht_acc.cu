@@ -331,11 +331,30 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         const unsigned lo_v = tr ? EX_W : EX_N, hi_v = tr ? EX_E : EX_S;
         // codes that do not link from this array column; bit 15: outside the raster; bit 0: code 0
         const unsigned cm = (u == 0 ? lo_u : 0u) | (u == lim_u - 1 ? hi_u : 0u) | (u >= lim_u ? 0xFFFFu : 0u) | 1u;
-        const int pk0 = tr ? (u + 1) * RP + XO + v0 : (v0 + 1) * RP + XO + u, pks = tr ? 4 : 4 * RP;
+        // packed bytes of the 16 cells.  As stored: a warp reads 32 consecutive bytes of a
+        // row.  Transposed: the cells are bytes v0, v0 + 4, ... of ONE raster row -- four
+        // 128-bit loads fetch the row, byte v0 of every word is a cell (byte loads down a
+        // column of the 96-byte pitch would be 6-way bank conflicts).
+        unsigned bw[CPT];
+        if (tr) {
+            const uint4 *row = reinterpret_cast<const uint4 *>(pk + (u + 1) * RP + XO);
+#pragma unroll
+            for (int q = 0; q < CPT / 4; q++) {
+                const uint4 w4 = row[q];
+                bw[4 * q] = w4.x; bw[4 * q + 1] = w4.y; bw[4 * q + 2] = w4.z; bw[4 * q + 3] = w4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; k++)
+                bw[k] = (bw[k] >> (8 * v0)) & 0xFFu;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; k++)
+                bw[k] = pk[(v0 + 1 + 4 * k) * RP + XO + u];
+        }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             const int v = v0 + 4 * k;
-            const unsigned b = pk[pk0 + k * pks];
+            const unsigned b = bw[k];
             const unsigned ex = cm | (v == 0 ? lo_v : 0u) | (v == lim_v - 1 ? hi_v : 0u) | (v >= lim_v ? 0xFFFFu : 0u);
             const unsigned code = b & HT_DIR_CODE;
             // no link: a stop flag, or the receiver is outside the tile / the raster
@@ -870,7 +889,7 @@ constexpr int SMF_BAR = SMF_LUT + 64;
 constexpr int SMF_TOTAL = SMF_BAR + 16;
 
 template <int WMODE>
-__global__ void __launch_bounds__(THREADS, 6)
+__global__ void __launch_bounds__(THREADS, 5) // 39 KB of shared memory per CTA: five fit an SM
 acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -955,17 +974,21 @@ acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     // ---- walkers: one per entry cell with inflow
     if (inflow) {
         const unsigned i_lo = (unsigned)(inflow & 0xFFFFu), i_hi = (unsigned)(inflow >> 16);
-        int cur = ely * CP + elx;
+        // The link (top byte of the low word) never changes: it is read with a plain byte
+        // load, and the adds are fire-and-forget REDs -- the walk's critical path is one
+        // LDS per step instead of a returning atomic.
+        unsigned addr = ht::smem_u32(lo32) + 4u * (unsigned)(ely * CP + elx);
         // a path visits a cell once; the bound only matters for a cyclic (corrupt)
         // direction raster, which must not hang the GPU
         for (int step = 0; step < T * T; step++) {
-            const unsigned old = atomicAdd(&lo32[cur], i_lo);
+            int off;
+            asm volatile("ld.shared.s8 %0, [%1 + 3];" : "=r"(off) : "r"(addr));
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(i_lo) : "memory");
             if (i_hi)
-                atomicAdd(&hi32[cur], i_hi);
-            const int off = (int)old >> 24;
+                asm volatile("red.shared.add.u32 [%0 + %2], %1;" ::"r"(addr), "r"(i_hi), "n"(SMF_HI - SMF_LO) : "memory");
             if (off == 0)
                 break;
-            cur += off;
+            addr += 4u * (unsigned)off;
         }
     }
     __syncthreads();
