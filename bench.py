@@ -517,14 +517,15 @@ def run_product(args):
     if pits or ties:
         raise SystemExit(f"synthetic DEM is not conditioned: {pits} pits, {ties} ties")
 
-    def step():
-        engine.flow_direction_accumulation()
-
     if world > 1:
         # NCCL sets up its channels lazily on the first collectives of each size; keep that
         # out of the W warm-up steps the caller asked for
         for _ in range(5):
-            step()
+            engine.flow_direction_accumulation()
+    # One step = every kernel, memset and collective of engine.flow_direction_accumulation(),
+    # captured once and replayed as ONE CUDA graph launch per step (BandEngine.graph): a
+    # sharded step is ~40 host calls, and 8 ranks share the box's host cores.
+    step = engine.graph(engine.flow_direction_accumulation)
     for _ in range(args.warmup):
         step()
     launches0 = engine.launches
@@ -538,6 +539,7 @@ def run_product(args):
         barrier()
     ms = e0.elapsed_time(e1) / max(args.steps, 1)
     launches = engine.launches - launches0
+    step.release()  # the graph holds NCCL state; the results stay in the engine's buffers
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -68,6 +68,8 @@ struct AccArgs {
     int64_t lacc64_ld;
     int32_t *tile_e;          // weighted mode: log2(tile unit / global unit) per tile
     const unsigned *gmax_bits; // weighted mode: bits of the raster's largest |weight| (float)
+    const uint8_t *tile_phase; // stage C of a sharded run: 1 = the tile's inflow depends on the
+    int phase;                 // neighbour bands' deliveries; only tiles of `phase` are processed
 };
 
 // row / column step of GRASS code 1..8 (2-bit tables: dr+1 = 0,0,0,1,2,2,2,1; dc+1 = 2,1,0,0,0,1,2,2)
@@ -742,6 +744,8 @@ __global__ void __launch_bounds__(THREADS, 3)
 acc_final_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (p.tile_phase && p.tile_phase[blockIdx.x] != p.phase)
+        return; // the other pass of a sharded run takes this tile
     uint8_t *pk = smem_raw; // 64 x 64, no ring
     uint32_t *wpl = reinterpret_cast<uint32_t *>(smem_raw + SMX_W); // [4][T * WP]
     uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + SMX_BAR);
@@ -893,6 +897,8 @@ __global__ void __launch_bounds__(THREADS, 5) // 39 KB of shared memory per CTA:
 acc_final_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (p.tile_phase && p.tile_phase[blockIdx.x] != p.phase)
+        return; // the other pass of a sharded run takes this tile
     uint8_t *pk = smem_raw; // 64 x 64, no ring
     uint32_t *lo32 = reinterpret_cast<uint32_t *>(smem_raw + SMF_LO);
     uint32_t *hi32 = reinterpret_cast<uint32_t *>(smem_raw + SMF_HI);
@@ -1112,12 +1118,29 @@ __device__ __forceinline__ i128 masked_plus(const i128 &old, const i128 &add)
 __device__ __forceinline__ bool is_marked(unsigned long long v) { return (v >> MARK_SHIFT) != 0ull; }
 __device__ __forceinline__ bool is_marked(const i128 &v) { return (v.lo & ((1ull << 24) - 1ull)) != 0ull; }
 
+// boundary-graph slot of column (tx, lx) of the band's first (side 0) / last (side 1) row
+__device__ __forceinline__ int32_t band_edge_slot_of(int side, int tx, int lx, int tiles_x, int tiles_y, int last_h)
+{
+    if (!side)
+        return tx * SLOTS + lx;
+    return ((tiles_y - 1) * tiles_x + tx) * SLOTS + (last_h == 1 ? lx : T + lx);
+}
+__device__ __forceinline__ bool is_band_edge_slot(int32_t u, int tiles_x, int tiles_y, int last_h)
+{
+    const int tile = u / SLOTS, k = u % SLOTS;
+    if (tile >= tiles_x * tiles_y)
+        return false; // a virtual slot (a neighbour band's cell)
+    const int ty = tile / tiles_x;
+    return (ty == 0 && k < T) || (ty == tiles_y - 1 && (last_h == 1 ? k < T : (k >= T && k < 2 * T)));
+}
+
 template <typename V>
 __global__ void __launch_bounds__(256, 4)
 coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int32_t *list,
                       const int *nlist, int32_t *idmap, int32_t *ptrA, int32_t *ptrB, V *a,
                       V *arr0, V *arr1, int32_t *rootA, int32_t *rootB, V *agg_out,
-                      int32_t *root_out, int *flags, int *rounds_out, int add_to_masked)
+                      int32_t *root_out, int *flags, int *rounds_out, int add_to_masked,
+                      int edge_tiles_x, int edge_tiles_y, int edge_last_h)
 {
     unsigned *gbar = reinterpret_cast<unsigned *>(flags + 96); // zeroed with flags
     unsigned epoch = 0;
@@ -1128,9 +1151,18 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
     if (list) {
         for (int64_t i = t0; i < na; i += stride)
             idmap[list[i]] = (int32_t)i;
-        if (root_out)
+        // slots that are not nodes end at themselves.  With an edge filter (row bands) only
+        // the slots of the band's first / last row are ever asked for
+        if (root_out && edge_tiles_x > 0) {
+            for (int64_t c = t0; c < 2ll * edge_tiles_x * T; c += stride) {
+                const int side = c >= (int64_t)edge_tiles_x * T, cc = (int)(c - (int64_t)side * edge_tiles_x * T);
+                const int32_t s = band_edge_slot_of(side, cc / T, cc % T, edge_tiles_x, edge_tiles_y, edge_last_h);
+                root_out[s] = s;
+            }
+        }
+        else if (root_out)
             for (int64_t s = t0; s < n; s += stride)
-                root_out[s] = (int32_t)s; // slots that are not nodes end at themselves
+                root_out[s] = (int32_t)s;
         grid_barrier(gbar, epoch);
     }
     for (int64_t i = t0; i < na; i += stride) {
@@ -1164,8 +1196,11 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
                 pt[j] = t[j] >= 0 ? ptrA[t[j]] : -1;
                 v[j] = t[j] >= 0 ? a[i] : (V)0;
                 d[j] = t[j] >= 0 ? prev[i] : (V)0;
+                // the last node of the path, written ONCE: in the round in which the node
+                // finishes (its target t has no pointer left, so t finished in an earlier
+                // round and root[t] is final), not carried through every round
                 if (rootA)
-                    rr[j] = t[j] >= 0 ? rootA[t[j]] : (t[j] == -1 ? rootA[i] : 0);
+                    rr[j] = (t[j] >= 0 && pt[j] < 0) ? rootA[t[j]] : -1;
             }
 #pragma unroll
             for (int j = 0; j < U; j++) {
@@ -1183,15 +1218,14 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
                     any = true;
                 }
                 ptrB[i] = pt[j];
-                if (rootA)
-                    rootB[i] = rr[j];
+                if (rootA && rr[j] >= 0)
+                    rootA[i] = rr[j];
             }
         }
         if (any)
             flags[round] = 1;
         grid_barrier(gbar, epoch);
         int32_t *tp = ptrA; ptrA = ptrB; ptrB = tp;
-        tp = rootA; rootA = rootB; rootB = tp;
         if (!flags[round] || round == 62)
             break;
     }
@@ -1202,7 +1236,8 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
         // delta resolve: the totals are a correction on top of an earlier result whose
         // upper 24 bits carried band-edge marks (u64 values only)
         agg_out[u] = add_to_masked ? masked_plus(agg_out[u], total) : total;
-        if (rootA && root_out)
+        if (rootA && root_out &&
+            (edge_tiles_x <= 0 || is_band_edge_slot((int32_t)u, edge_tiles_x, edge_tiles_y, edge_last_h)))
             root_out[u] = list ? list[rootA[i]] : rootA[i];
     }
     if (t0 == 0 && rounds_out)
@@ -1267,6 +1302,20 @@ __global__ void marked_nodes_kernel(const V *agg, const int32_t *list,
 // row of the band above / below (marks cleared); out[2 / 3][c] = for the band's own
 // first / last row cell c, the foreign cell the path entering there finally
 // reaches (side * cols + column, side 0 = band above), or -1.
+// Sharded runs: a tile whose entry slots carry no mark receives nothing that depends on the
+// neighbour bands, so its stage C can run while the band tables are being exchanged.
+template <typename V>
+__global__ void tile_phase_kernel(const V *agg, const int32_t *list, const int *nlist, int ntile_slots,
+                                  uint8_t *tile_phase)
+{
+    const int na = *nlist;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na; i += gridDim.x * blockDim.x) {
+        const int32_t u = list[i];
+        if (u < ntile_slots && is_marked(agg[u]))
+            tile_phase[u / SLOTS] = 1; // every writer stores the same byte
+    }
+}
+
 __global__ void band_tables_kernel(const unsigned long long *agg, const int32_t *root, int64_t rows,
                                    int64_t cols, int tiles_x, int tiles_y, int64_t vfirst,
                                    long long *out)
@@ -1556,7 +1605,8 @@ int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int
                    const int *nlist, int32_t *idmap, int32_t *ptrA, int32_t *ptrB, void *a_,
                    void *arr0_, void *arr1_, int32_t *rootA, int32_t *rootB, void *agg_out_,
                    int32_t *root_out, int *flags, int *rounds_dev, cudaStream_t st,
-                   int add_to_masked = 0)
+                   int add_to_masked = 0, int ctas_per_sm = 0, int edge_tiles_x = 0,
+                   int edge_tiles_y = 0, int edge_last_h = 0)
 {
     auto kern = coarse_resolve_kernel<V>;
     int per_sm = 0;
@@ -1566,6 +1616,10 @@ int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int
     int dev = 0, sms = 0;
     HT_CUDA_TRY(cudaGetDevice(&dev));
     HT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // the delta resolve of a sharded run visits a few per cent of the nodes and shares the
+    // GPU with stage C of the tiles it does not touch: one CTA per SM is plenty
+    if (ctas_per_sm > 0 && per_sm > ctas_per_sm)
+        per_sm = ctas_per_sm;
     int grid = sms * per_sm;
     const int64_t need = (n + 255) / 256;
     if (grid > need)
@@ -1575,7 +1629,8 @@ int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int
     const V *b0 = (const V *)base0;
     V *a = (V *)a_, *arr0 = (V *)arr0_, *arr1 = (V *)arr1_, *agg_out = (V *)agg_out_;
     void *args[] = {&b0, &next0, &n, &list, &nlist, &idmap, &ptrA, &ptrB, &a, &arr0, &arr1,
-                    &rootA, &rootB, &agg_out, &root_out, &flags, &rounds_dev, &add_to_masked};
+                    &rootA, &rootB, &agg_out, &root_out, &flags, &rounds_dev, &add_to_masked,
+                    &edge_tiles_x, &edge_tiles_y, &edge_last_h};
     HT_CUDA_TRY(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(256), args, 0, st));
     return 0;
 }
@@ -1596,6 +1651,7 @@ int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t tota
     p.lacc = nullptr; p.lacc_ld = 0; p.packed = nullptr; p.packed_ld = 0;
     p.list = nullptr; p.nlist = nullptr;
     p.lacc64 = nullptr; p.lacc64_ld = 0; p.tile_e = nullptr; p.gmax_bits = nullptr;
+    p.tile_phase = nullptr; p.phase = 0;
     return 0;
 }
 
@@ -1708,14 +1764,17 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
     int32_t *rA = want_roots ? wk.rootA : nullptr, *rC = want_roots ? wk.rootC : nullptr;
     int32_t *rOut = want_roots ? wk.rootB : nullptr;
     HT_CUDA_TRY(cudaMemsetAsync(wk.aggB, 0, wk.nslots * wk.vsize, (cudaStream_t)stream));
+    // the last node of a path is only ever asked for at the slots of the band's first / last row
+    const int etx = want_roots ? ht::cdiv(cols, T) : 0, ety = ht::cdiv(rows, T);
+    const int elh = (int)(rows - (int64_t)(ety - 1) * T);
     if (mode == W_F32)
         return launch_resolve<i128>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist, wk.idmap,
                                     wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1, rA, rC, wk.aggB,
-                                    rOut, wk.flags, rounds_dev, (cudaStream_t)stream);
+                                    rOut, wk.flags, rounds_dev, (cudaStream_t)stream, 0, 0, etx, ety, elh);
     return launch_resolve<unsigned long long>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist,
                                               wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
                                               rA, rC, wk.aggB, rOut, wk.flags, rounds_dev,
-                                              (cudaStream_t)stream);
+                                              (cudaStream_t)stream, 0, 0, etx, ety, elh);
 }
 
 // Row-band sharding, count modes, after ht_acc_local: tag the slots of the band's first
@@ -1794,7 +1853,7 @@ extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode, const 
         HT_LAUNCH_CHECK();
         return launch_resolve<i128>(wk.base2, wk.next0, wk.nslots, wk.list2, wk.nlist2, wk.idmap, wk.ptrA,
                                     wk.ptrB, wk.aggA, wk.arr0, wk.arr1, nullptr, nullptr, wk.aggB, nullptr,
-                                    wk.flags, nullptr, st, 1);
+                                    wk.flags, nullptr, st, 1, 1);
     }
     marked_nodes_kernel<unsigned long long><<<ht::kSMs * 4, 256, 0, st>>>(
         (const unsigned long long *)wk.aggB, wk.list, wk.nlist, wk.list2, wk.nlist2,
@@ -1804,7 +1863,7 @@ extern "C" int ht_acc_resolve_delta(int64_t rows, int64_t cols, int mode, const 
     return launch_resolve<unsigned long long>(wk.base2, wk.next0, wk.nslots, wk.list2, wk.nlist2,
                                               wk.idmap, wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
                                               nullptr, nullptr, wk.aggB, nullptr, wk.flags, nullptr,
-                                              st, 1);
+                                              st, 1, 1);
 }
 
 extern "C" int ht_band_tables(int64_t rows, int64_t cols, int mode, void *ws, size_t ws_bytes,
@@ -1904,11 +1963,13 @@ extern "C" int ht_forest_resolve(const void *base, const int32_t *next, int64_t 
 
 
 // Stage C.
-extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows,
-                            int64_t cols, int64_t row0, int64_t total_rows, int halo_top,
-                            int halo_bot, int mode, const float *w, int64_t w_ld, int has_wnd,
-                            float wnd, double *acc, int64_t acc_ld, int8_t *dir_out,
-                            int64_t dir_ld, void *ws, size_t ws_bytes, void *stream)
+// `phase` < 0: every tile.  0 / 1 (after ht_acc_tile_phases): only the tiles whose inflow does
+// not / does depend on the neighbour bands' deliveries.
+extern "C" int ht_acc_final_phase(const uint8_t *packed, int64_t packed_ld, int64_t rows,
+                                  int64_t cols, int64_t row0, int64_t total_rows, int halo_top,
+                                  int halo_bot, int mode, const float *w, int64_t w_ld, int has_wnd,
+                                  float wnd, double *acc, int64_t acc_ld, int8_t *dir_out,
+                                  int64_t dir_ld, void *ws, size_t ws_bytes, int phase, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (rows == 0 || cols == 0)
@@ -1939,7 +2000,50 @@ extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t ro
     p.inflow = wk.aggB;
     p.w = w; p.w_ld = w_ld; p.has_wnd = has_wnd; p.wnd = wnd;
     p.acc = acc; p.acc_ld = acc_ld; p.dir_out = dir_out; p.dir_ld = dir_ld;
+    if (phase >= 0) {
+        p.tile_phase = reinterpret_cast<const uint8_t *>(wk.rootC);
+        p.phase = phase ? 1 : 0;
+    }
     return dispatch_tile<true>(mode, map, p, st);
+}
+
+extern "C" int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows,
+                            int64_t cols, int64_t row0, int64_t total_rows, int halo_top,
+                            int halo_bot, int mode, const float *w, int64_t w_ld, int has_wnd,
+                            float wnd, double *acc, int64_t acc_ld, int8_t *dir_out,
+                            int64_t dir_ld, void *ws, size_t ws_bytes, void *stream)
+{
+    return ht_acc_final_phase(packed, packed_ld, rows, cols, row0, total_rows, halo_top, halo_bot,
+                              mode, w, w_ld, has_wnd, wnd, acc, acc_ld, dir_out, dir_ld, ws,
+                              ws_bytes, -1, stream);
+}
+
+// Sharded runs, after ht_acc_resolve(want_roots = 1) on a graph whose band-edge slots were
+// marked (ht_acc_mark_edges): one byte per tile, 1 = an entry slot of the tile carries a mark.
+extern "C" int ht_acc_tile_phases(int64_t rows, int64_t cols, int mode, void *ws, size_t ws_bytes,
+                                  void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows <= 0 || cols <= 0)
+        return HT_OK;
+    if (mode < 0 || mode > 2)
+        return HT_ERR_ARG;
+    Workspace wk;
+    int rc = carve(ws, ws_bytes, rows, cols, mode, wk);
+    if (rc)
+        return rc;
+    const int ntiles = ht::cdiv(rows, T) * ht::cdiv(cols, T);
+    uint8_t *ph = reinterpret_cast<uint8_t *>(wk.rootC);
+    HT_CUDA_TRY(cudaMemsetAsync(ph, 0, (size_t)ntiles, st));
+    const int grid = ht::kSMs * 8;
+    if (mode == W_F32)
+        tile_phase_kernel<i128><<<grid, 256, 0, st>>>((const i128 *)wk.aggB, wk.list, wk.nlist,
+                                                      ntiles * SLOTS, ph);
+    else
+        tile_phase_kernel<unsigned long long><<<grid, 256, 0, st>>>(
+            (const unsigned long long *)wk.aggB, wk.list, wk.nlist, ntiles * SLOTS, ph);
+    HT_LAUNCH_CHECK();
+    return HT_OK;
 }
 
 // Stages A + B + C on one device.

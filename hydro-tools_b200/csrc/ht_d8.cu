@@ -27,6 +27,8 @@
 //    per-cell rule (seeds, NULL neighbours, taint flag) runs as three passes
 //    through shared memory.
 // 4 B read + 1 B written per cell (5 B/cell algorithmic).
+#include <atomic>
+
 #include "ht_common.cuh"
 
 namespace {
@@ -61,6 +63,7 @@ struct D8Args {
     uint8_t *packed;
     int64_t packed_ld;
     unsigned long long *counters; // [0] pits, [1] ties, [2] elevations out of range
+    unsigned *next_tile;          // dynamic tile scheduler of this launch (zeroed before it)
 };
 
 // r.watershed's neighbour order ct = 0..7: S,N,W,E,NE,SW,SE,NW (cardinals first)
@@ -246,12 +249,18 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
     __shared__ __align__(16) uint8_t tmap[DH * DP]; // 1 where a re-pointed seed drains into the cell
     __shared__ int any_edge;
 
+    // Tiles are handed out by a counter, not by a fixed stride: a CTA that starts late (a
+    // collective's kernel held its SM when the grid launched) then simply takes fewer tiles
+    // instead of finishing its fixed share late.  A CTA's first tile is blockIdx.x.
+    __shared__ int stile[STAGES];
     const int tid = threadIdx.x;
     const int ntiles = p.tiles_x * p.tiles_y;
     if (tid == 0) {
         ht::tma_prefetch_desc(&map);
-        for (int s = 0; s < STAGES; s++)
+        for (int s = 0; s < STAGES; s++) {
             ht::mbar_init(&full[s], 1);
+            stile[s] = s == 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(p.next_tile, 1u));
+        }
         ht::fence_mbar_init();
     }
     __syncthreads();
@@ -263,16 +272,17 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
                         ty * TH - 2 + p.halo_top, &full[s]);
     };
     if (tid == 0)
-        for (int s = 0; s < STAGES; s++) {
-            const int t = blockIdx.x + s * gridDim.x;
-            if (t < ntiles)
-                issue(t, s);
-        }
+        for (int s = 0; s < STAGES; s++)
+            if (stile[s] < ntiles)
+                issue(stile[s], s);
 
     unsigned pits = 0, ties = 0, range = 0;
-    int k = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+    for (int k = 0;; k++) {
         const int s = k % STAGES;
+        // written by thread 0 before the barriers of the previous iteration / of the prologue
+        const int tile = stile[s];
+        if (tile >= ntiles)
+            break; // the counter only grows: every later stage is past the end as well
         int32_t *alt = reinterpret_cast<int32_t *>(smem_raw + (size_t)s * STAGE_STRIDE);
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int64_t x0 = (int64_t)tx * TW, y0 = (int64_t)ty * TH;
@@ -469,7 +479,8 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
         ht::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            const int next = tile + STAGES * gridDim.x;
+            const int next = (int)(gridDim.x + atomicAdd(p.next_tile, 1u));
+            stile[s] = next;
             if (next < ntiles)
                 issue(next, s);
         }
@@ -508,15 +519,24 @@ int setup(const float *dem, int64_t rows, int64_t cols, int64_t ld, int has_noda
     p.inv_ew = (float)(1.0 / p.ew); p.inv_ns = (float)(1.0 / p.ns);
     p.inv_diag = (float)(1.0 / p.diag);
     p.r_ew = (float)(p.diag / p.ew); p.r_ns = (float)(p.diag / p.ns);
-    p.packed = nullptr; p.packed_ld = 0; p.counters = nullptr;
+    p.packed = nullptr; p.packed_ld = 0; p.counters = nullptr; p.next_tile = nullptr;
     const float *base = dem - (int64_t)p.halo_top * ld;
     return ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,
                            rows + p.halo_top + p.halo_bot, cols, ld, BW, BH, true);
 }
 
+// One scheduler counter per launch in flight: a ring of 256, so that launches on different
+// streams (or queued behind each other) never share one.
+__device__ unsigned g_next_tile[256];
+
 template <bool VALIDATE>
-int launch(const CUtensorMap &map, const D8Args &p, cudaStream_t st)
+int launch(const CUtensorMap &map, D8Args p, cudaStream_t st)
 {
+    static std::atomic<unsigned> ring{0};
+    unsigned *counters = nullptr;
+    HT_CUDA_TRY(cudaGetSymbolAddress((void **)&counters, g_next_tile));
+    p.next_tile = counters + (ring.fetch_add(1u) & 255u);
+    HT_CUDA_TRY(cudaMemsetAsync(p.next_tile, 0, sizeof(unsigned), st));
     auto kern = d8_kernel<VALIDATE>;
     const size_t smem = (size_t)STAGES * STAGE_STRIDE;
     HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

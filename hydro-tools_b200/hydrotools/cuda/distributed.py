@@ -165,6 +165,42 @@ class BandEngine:
             band.apply_sign()
             self.launches += band.take_launches()
 
+    def graph(self, fn, warmup: int = 3):
+        """Capture one call of ``fn`` (a method of this engine working on its resident
+        buffers, e.g. ``engine.flow_direction_accumulation``) into a CUDA graph and return
+        ``replay()``.  A sharded step is ~40 launches, memsets and two collectives; at 2 ms
+        per step the host cannot enqueue them as fast as the GPU retires them (8 ranks share
+        the box's cores), one graph launch can.  The NCCL collectives and the side-stream
+        fork / join of the step are captured with it (every rank must capture and replay in
+        step).  Buffers are the engine's own: results() after replay() reads the last step."""
+        cap = torch.cuda.Stream(device=self.band.dev)
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            for _ in range(max(warmup, 1)):  # lazy state: TMA encoder, NCCL channels, side stream
+                fn()
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        l0 = self.launches
+        g = torch.cuda.CUDAGraph()
+        # thread_local: NCCL's watchdog thread polls its events while this thread captures
+        with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+            fn()
+        per_replay = self.launches - l0
+        self.launches = l0
+
+        def replay():
+            g.replay()
+            self.launches += per_replay
+        def release():
+            # a process group cannot be torn down while a graph still holds its collectives
+            torch.cuda.synchronize()
+            g.reset()
+        replay.graph = g
+        replay.release = release
+        return replay
+
     def load_direction(self, direction):
         """A STORED direction raster (this rank's rows; int8 GRASS codes, -128 NULL) instead
         of a DEM: FlowAccumulation(direction), /root/reference/src/hydrotools/watershed.py:
@@ -228,6 +264,28 @@ class BandEngine:
                 # that the second one only visits the nodes downstream of the band edge
                 band.mark_edges(mode)
             band.resolve(True)
+            if delta and hasattr(band, "final_phase"):
+                # Stage C in two passes.  Only the tiles with a marked entry slot (the ones on
+                # or downstream of the band's first / last row) depend on what the neighbour
+                # bands deliver: the others are written on the main stream while the tables
+                # travel and the band-level forest and the delta resolve run on a side stream.
+                band.tile_phases(mode)
+                mine = band.publish_tables(mode)  # [4 or 6, cols] int64
+                main = torch.cuda.current_stream()
+                side = band.side_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    every = torch.empty((P * mine.shape[0], self.cols), dtype=torch.int64,
+                                        device=mine.device)
+                    dist.all_gather_into_tensor(every, mine, group=self.group)
+                    band.import_flows(every, P, self.rank, mode, delta)
+                    every.record_stream(side)
+                mine.record_stream(side)
+                band.final_phase(0, mode, want_dir)
+                main.wait_stream(side)
+                band.final_phase(1, mode, want_dir)
+                self.launches += band.take_launches()
+                return
             mine = band.publish_tables(mode)  # [4 or 6, cols] int64
             every = torch.empty((P * mine.shape[0], self.cols), dtype=torch.int64, device=mine.device)
             dist.all_gather_into_tensor(every, mine, group=self.group)
@@ -519,6 +577,31 @@ class CudaBand:
                     self.dir.data_ptr() if (want_dir and mode == 0) else None, self.dld,
                     ws.data_ptr(), ws.numel(), self.D.stream_ptr())
         self._launches += 1
+
+    def tile_phases(self, mode=0):
+        """After resolve(True) on a marked graph: one byte per tile, 1 = the tile's inflow
+        depends on the neighbour bands' deliveries (an entry slot carries a mark)."""
+        ws = self._wsm(mode)
+        self.N.call("ht_acc_tile_phases", self.rows, self.cols, mode, ws.data_ptr(), ws.numel(),
+                    self.D.stream_ptr())
+        self._launches += 1
+
+    def final_phase(self, phase, mode=0, want_dir=True):
+        """Stage C of the tiles of one phase (see tile_phases)."""
+        w, wld, has, nd = self._wargs(mode)
+        ws = self._wsm(mode)
+        self.N.call("ht_acc_final_phase", self._packed0(), self.pld, self.rows, self.cols, self.row0,
+                    self.total_rows, int(self.htop > 0), int(self.hbot > 0), mode, w, wld, has, nd,
+                    self.acc.data_ptr(), self.ald,
+                    self.dir.data_ptr() if (want_dir and mode == 0) else None, self.dld,
+                    ws.data_ptr(), ws.numel(), int(phase), self.D.stream_ptr())
+        self._launches += 1
+
+    def side_stream(self):
+        """High-priority stream for the table exchange chain of a sharded accumulation."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.dev, priority=-1)
+        return self._side
 
     MARK = 1 << 40  # band-edge mark in the u64 sums of the boundary graph (csrc/ht_acc.cu)
 

@@ -201,6 +201,19 @@ int ht_acc_final(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t
                  int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
                  double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld, void *ws,
                  size_t ws_bytes, void *stream);
+/* row-band sharding: stage C in two passes, so that most of it runs while the band tables
+ * travel.  ht_acc_tile_phases (after ht_acc_resolve on a marked graph) leaves one byte per
+ * tile: 1 = an entry slot of the tile carries a band-edge mark, i.e. its inflow changes with
+ * what the neighbour bands deliver.  ht_acc_final_phase(phase = 0) writes the tiles that do
+ * not depend on the exchange, phase = 1 (after ht_acc_resolve_delta) the others; phase < 0 =
+ * every tile (= ht_acc_final). */
+int ht_acc_tile_phases(int64_t rows, int64_t cols, int mode, void *ws, size_t ws_bytes,
+                       void *stream);
+int ht_acc_final_phase(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
+                       int64_t row0, int64_t total_rows, int halo_top, int halo_bot,
+                       int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
+                       double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld, void *ws,
+                       size_t ws_bytes, int phase, void *stream);
 int ht_acc_f64(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
                int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
                double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld, void *ws,

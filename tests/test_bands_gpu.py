@@ -53,6 +53,8 @@ def accumulate_bands(bands, mode=0, delta=False, direction=True):
         if delta:
             band.mark_edges(mode)
         band.resolve(True)
+        if delta:
+            band.tile_phases(mode)
         if not weighted:
             tabs.append(band.band_tables(mode))
     if weighted or delta:
@@ -67,6 +69,13 @@ def accumulate_bands(bands, mode=0, delta=False, direction=True):
                 assert torch.equal(every[4 * b + 2:4 * b + 4], tabs[b][1].to(torch.int64))
             base2, nxt2 = bands[0].band_graph(every, P)
             assert torch.equal(base2, base) and torch.equal(nxt2, nxt)
+        if delta:
+            # stage C of the tiles that do not depend on the neighbour bands runs BEFORE the
+            # imports arrive (BandEngine overlaps the two); poison the outputs first
+            for band in bands:
+                band.acc.fill_(-7.0)
+                band.dir.fill_(99)
+                band.final_phase(0, mode)
         for b, band in enumerate(bands):
             band.import_flows(every, P, b, mode, delta)
     else:
@@ -79,7 +88,10 @@ def accumulate_bands(bands, mode=0, delta=False, direction=True):
             band.resolve(False)
     outs = []
     for band in bands:
-        band.final(mode)
+        if delta:
+            band.final_phase(1, mode)
+        else:
+            band.final(mode)
         fd, fa = band.results()
         outs.append((fd.cpu().numpy(), fa.cpu().numpy()))
     return np.vstack([o[0] for o in outs]), np.vstack([o[1] for o in outs])

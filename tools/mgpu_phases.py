@@ -42,6 +42,15 @@ for it in range(10):
     for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
         tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
 dist.barrier()
+# tiles whose inflow depends on what the neighbour bands deliver (a marked entry slot)
+band.local(0); band.mark_edges(0); band.resolve(True)
+tiles = ((rows + 63) // 64) * ((cols + 63) // 64)
+agg = band._ws_view(2, torch.int64)[:tiles * 256].view(tiles, 256)
+aff = ((agg >> 40) != 0).any(dim=1)
+print(f"rank {rank}: {int(aff.sum())} of {tiles} tiles carry a marked entry "
+      f"({100.0 * float(aff.float().mean()):.1f} %); per tile row (first 12, last 4): "
+      f"{[round(float(x), 2) for x in aff.view((rows + 63) // 64, -1).float().mean(dim=1)[:12]]} ... "
+      f"{[round(float(x), 2) for x in aff.view((rows + 63) // 64, -1).float().mean(dim=1)[-4:]]}", flush=True)
 names = list(tot.keys())
 mine = torch.tensor([tot[k] / 10 for k in names], dtype=torch.float64, device="cuda")
 allr = [torch.empty_like(mine) for _ in range(world)]
