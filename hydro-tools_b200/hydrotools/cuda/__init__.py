@@ -25,6 +25,7 @@ from .streams import (  # noqa: F401
     upstream_mean,
     upstream_stats,
 )
+from .pipeline import FlowPipeline, flow_direction_accumulation_many  # noqa: F401
 from .watershed import (  # noqa: F401
     FlowAccumulation,
     flow_accumulation_arrays,
@@ -40,6 +41,8 @@ __all__ = [
     "terrain",
     "flow_direction_accumulation",
     "flow_direction_accumulation_arrays",
+    "flow_direction_accumulation_many",
+    "FlowPipeline",
     "FlowAccumulation",
     "flow_accumulation_arrays",
     "validate_conditioned",
