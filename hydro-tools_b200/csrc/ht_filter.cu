@@ -468,6 +468,160 @@ run_filter_tiled_kernel(const float *src, int64_t ld, int64_t rows, int64_t cols
     }
 }
 
+// Self-contained variant for kernels whose staged block fits shared memory (discs up to a
+// radius of ~25): the CTA reads the RAW tile plus halo (4 B per staged cell instead of 12 B of
+// global prefix entries, and no prefix pass over the raster at all), builds the row prefix
+// sums LOCALLY -- a run difference does not care where the prefix starts -- and, when no
+// staged cell is invalid and the block lies inside the raster, skips the counts: n is then
+// the number of selected cells.  Local prefixes are also shorter sums, i.e. more accurate.
+constexpr int MAX_LOCAL_RUNS = 128;
+struct LocalRuns {
+    int n, cells;                 // runs, selected cells
+    int off_a[MAX_LOCAL_RUNS];    // ky * C + a       (prefix sums, pitch C)
+    int off_b[MAX_LOCAL_RUNS];    // ky * C + b + 1
+    int cnt_a[MAX_LOCAL_RUNS];    // ky * bw + a      (counts, pitch bw)
+    int cnt_b[MAX_LOCAL_RUNS];    // ky * bw + b + 1
+};
+
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32(uint32_t addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+template <int TH_, int KU>
+__global__ void __launch_bounds__(256)
+run_filter_local_kernel(const __grid_constant__ CUtensorMap map, const float *src, int64_t ld,
+                        int64_t rows, int64_t cols, int halo_top, int has_nodata, float nodata,
+                        const __grid_constant__ LocalRuns runs, int i_start, int shift, int hx0a,
+                        int mean, float *out, int64_t out_ld, int R, int C, int bw)
+{
+    constexpr int th = TH_, HALF = TH_ / 2;
+    // sP: R x C doubles.  Behind it the raw box (R x bw floats, one TMA load, NaN outside the
+    // raster); the counts of a row overwrite that row's raw values once the row is scanned.
+    // (a name of its own: the 16-byte alignment of the other kernel's `fsm` would win)
+    extern __shared__ __align__(128) unsigned char lsm[];
+    __shared__ __align__(8) uint64_t bar;
+    float *raw = reinterpret_cast<float *>(lsm);
+    unsigned *sC = reinterpret_cast<unsigned *>(lsm);
+    double *sP = reinterpret_cast<double *>(lsm + (((size_t)R * bw * 4 + 127) / 128) * 128);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t x0 = (int64_t)blockIdx.x * 128, y0 = (int64_t)blockIdx.y * th;
+    if (tid == 0) {
+        ht::tma_prefetch_desc(&map);
+        ht::mbar_init(&bar, 1);
+        ht::fence_mbar_init();
+        ht::mbar_expect_tx(&bar, (uint32_t)(R * bw * 4));
+        ht::tma_load_2d(raw, &map, (int)x0 - hx0a, (int)y0 - i_start + halo_top, &bar);
+    }
+    __syncthreads();
+    ht::mbar_wait(&bar, 0);
+    // ---- row prefixes over the C - 1 raw cells of a row: warp -> rows, lane -> K consecutive cells
+    const int K = (C - 1 + 31) / 32; // <= KU
+    bool dirty = false;
+    for (int rr = warp; rr < R; rr += 8) {
+        float f[KU];
+        double run = 0.0;
+        unsigned cnt = 0u;
+#pragma unroll
+        for (int k = 0; k < KU; k++) {
+            const int cc = lane * K + k;
+            f[k] = __int_as_float(0x7fc00000);
+            if (k < K && cc < C - 1) {
+                f[k] = raw[rr * bw + shift + cc];
+                const bool ok = f[k] == f[k] && !(has_nodata && f[k] == nodata);
+                if (!ok)
+                    f[k] = __int_as_float(0x7fc00000);
+                dirty |= !ok;
+                run += ok ? (double)f[k] : 0.0;
+                cnt += ok ? 1u : 0u;
+            }
+        }
+        double ws = run;
+        unsigned wc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double s2 = __shfl_up_sync(0xffffffffu, ws, o);
+            const unsigned c2 = __shfl_up_sync(0xffffffffu, wc, o);
+            if (lane >= o) {
+                ws += s2;
+                wc += c2;
+            }
+        }
+        double base = ws - run; // exclusive prefix of the lane
+        unsigned cbase = wc - cnt;
+        __syncwarp(); // every lane has read its raw cells: the row now becomes the counts
+        if (lane == 0) {
+            sP[rr * C] = 0.0;
+            sC[rr * bw] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < KU; k++) {
+            const int cc = lane * K + k;
+            if (k < K && cc < C - 1) {
+                if (f[k] == f[k]) {
+                    base += (double)f[k];
+                    cbase += 1u;
+                }
+                sP[rr * C + cc + 1] = base;
+                sC[rr * bw + cc + 1] = cbase;
+            }
+        }
+    }
+    const bool clean = !__syncthreads_or(dirty);
+    const int lx = tid & 127;
+    const int64_t x = x0 + lx;
+    if (x >= cols)
+        return;
+    // thread -> one column, HALF consecutive rows; runs in the OUTER loop, so that a run's
+    // offsets are fetched once for the thread's rows.  32-bit shared addresses, stepped by
+    // the row pitch: two loads, two adds and two fp64 adds per cell and run.
+    const int ly0 = (tid >> 7) * HALF;
+    double sum[HALF];
+    unsigned n[HALF];
+#pragma unroll
+    for (int c = 0; c < HALF; c++) {
+        sum[c] = 0.0;
+        n[c] = clean ? (unsigned)runs.cells : 0u;
+    }
+    const uint32_t aP = ht::smem_u32(sP) + 8u * (unsigned)(ly0 * C + lx), stepP = 8u * (unsigned)C;
+    const uint32_t aC = ht::smem_u32(sC) + 4u * (unsigned)(ly0 * bw + lx), stepC = 4u * (unsigned)bw;
+    if (clean) {
+        for (int r = 0; r < runs.n; r++) {
+            uint32_t pb = aP + 8u * (unsigned)runs.off_b[r], pa = aP + 8u * (unsigned)runs.off_a[r];
+#pragma unroll
+            for (int c = 0; c < HALF; c++, pb += stepP, pa += stepP)
+                sum[c] += lds_f64(pb) - lds_f64(pa);
+        }
+    } else {
+        for (int r = 0; r < runs.n; r++) {
+            uint32_t pb = aP + 8u * (unsigned)runs.off_b[r], pa = aP + 8u * (unsigned)runs.off_a[r];
+            uint32_t cb = aC + 4u * (unsigned)runs.cnt_b[r], ca = aC + 4u * (unsigned)runs.cnt_a[r];
+#pragma unroll
+            for (int c = 0; c < HALF; c++, pb += stepP, pa += stepP, cb += stepC, ca += stepC) {
+                sum[c] += lds_f64(pb) - lds_f64(pa);
+                n[c] += lds_u32(cb) - lds_u32(ca);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < HALF; c++) {
+        const int64_t y = y0 + ly0 + c;
+        if (y >= rows)
+            break;
+        const float centre = src[y * ld + x];
+        const bool ok = centre == centre && !(has_nodata && centre == nodata) && n[c];
+        out[y * out_ld + x] = ok ? (float)(mean ? sum[c] / (double)n[c] : sum[c]) : __int_as_float(0x7fc00000);
+    }
+}
+
 template <int METHOD>
 int launch(const CUtensorMap &map, const FilterArgs &p, cudaStream_t st)
 {
@@ -589,6 +743,44 @@ extern "C" int ht_window_filter_runs_f32(const float *src, int64_t rows, int64_t
         }
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // kernels whose staged block fits shared memory: local prefixes, no pass over the raster
+    if (n_runs <= MAX_LOCAL_RUNS && kw <= 100) {
+        const int i_start = kh / 2, j_start = kw / 2, j_end = kw - 1 - j_start;
+        const int hx0a = (j_start + 3) / 4 * 4; // the TMA box starts on a 16-byte boundary
+        for (int th = 32; th >= 8; th >>= 1) {
+            const int R = th + kh - 1, C = 128 + kw;
+            const int bw = (std::max(128 + hx0a + (j_end + 3) / 4 * 4, C) + 3) / 4 * 4;
+            const size_t need = ((size_t)R * bw * 4 + 127) / 128 * 128 + (size_t)R * C * 8;
+            if (need > (th == 32 ? 110u : 200u) * 1024u || bw > 256 || R > 256)
+                continue;
+            CUtensorMap map;
+            if (ht::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src - (int64_t)halo_top * ld,
+                                rows_all, cols, ld, bw, R, true))
+                break; // rows not 16-byte aligned: the prefix path below takes any layout
+            LocalRuns lr;
+            lr.n = n_runs;
+            lr.cells = 0;
+            for (int r = 0; r < n_runs; r++) {
+                lr.off_a[r] = hruns[r].ky * C + hruns[r].a;
+                lr.off_b[r] = hruns[r].ky * C + hruns[r].b + 1;
+                lr.cnt_a[r] = hruns[r].ky * bw + hruns[r].a;
+                lr.cnt_b[r] = hruns[r].ky * bw + hruns[r].b + 1;
+                lr.cells += hruns[r].b - hruns[r].a + 1;
+            }
+            delete[] hruns;
+            const bool k5 = (C - 1 + 31) / 32 <= 5; // cells per lane in the row scans
+            auto kern = th == 32 ? (k5 ? run_filter_local_kernel<32, 5> : run_filter_local_kernel<32, 8>)
+                        : th == 16 ? (k5 ? run_filter_local_kernel<16, 5> : run_filter_local_kernel<16, 8>)
+                                   : (k5 ? run_filter_local_kernel<8, 5> : run_filter_local_kernel<8, 8>);
+            HT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            dim3 tgrid((unsigned)ht::cdiv(cols, 128), (unsigned)ht::cdiv(rows, th));
+            kern<<<tgrid, 256, need, st>>>(map, src, ld, rows, cols, halo_top,
+                                          has_nodata && nodata == nodata, nodata, lr, i_start,
+                                          hx0a - j_start, hx0a, method == M_MEAN, out, out_ld, R, C, bw);
+            HT_LAUNCH_CHECK();
+            return HT_OK;
+        }
+    }
     const int64_t pld = (cols + 2) / 2 * 2;
     uint8_t *b = (uint8_t *)(((uintptr_t)ws + 255) / 256 * 256);
     double *P = (double *)b;

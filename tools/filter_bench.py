@@ -54,3 +54,24 @@ for r in (10, 50, 100):
     ms = e0.elapsed_time(e1) / 3
     print(f"disc r={r:<3d} mean (prefix sums) {int(k.sum()):6d} cells  {ms:8.3f} ms  {n * n / ms / 1e6:8.1f} Gcells/s  "
           f"{n * n * int(k.sum()) / ms / 1e9:8.1f} Gsamples/ms equivalent")
+
+
+# the same through the C-ABI entry alone (no upload / allocation around it)
+ws = torch.empty(int(N.lib.ht_window_filter_runs_workspace_bytes(n, n, 201)), dtype=torch.uint8, device="cuda")
+for r in (5, 10, 20):
+    k = np.ascontiguousarray(disc(r))
+
+    def run():
+        N.call("ht_window_filter_runs_f32", dem.data_ptr(), n, n, ld, 0, 0.0, k.ctypes.data_as(C.c_void_p),
+               k.shape[0], k.shape[1], 4, out.data_ptr(), ld, 0, 0, ws.data_ptr(), ws.numel(), st)
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"disc r={r:<3d} mean, ht_window_filter_runs_f32 alone {int(k.sum()):6d} cells  {ms:8.3f} ms  "
+          f"{n * n / ms / 1e6:8.1f} Gcells/s  {n * n * 8 / ms / 1e6:7.0f} GB/s (8 B/cell)")
