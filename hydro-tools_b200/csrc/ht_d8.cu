@@ -321,7 +321,10 @@ d8_kernel(const __grid_constant__ CUtensorMap map, const D8Args p)
                     const bool nd = p.has_nodata && z[j] == p.nodata;
                     float a = F_INVALID;
                     if (small && !nd) {
-                        // rule R1: (int)(z * 1000 +- 0.5) in double; the half takes z's sign
+                        // rule R1: (int)(z * 1000 +- 0.5) in double; the half takes z's sign.
+                        // (An exact fp32 formulation -- product, FMA residual, rint and two
+                        // half-way tests -- was measured: 0.38 ms against 0.34, the kernel is
+                        // bound by instruction issue and the fp64 / conversion pipes are idle.)
                         const double half = __hiloint2double(
                             0x3FE00000 | (int)(__float_as_uint(z[j]) & 0x80000000u), 0);
                         a = (float)(int)((double)z[j] * 1000.0 + half);

@@ -433,3 +433,23 @@ def test_natural_terrain_conditioned_by_rank(hc):
     bfd, bfa = run_bands(dem, [0, 300, 640, 1100], None, 10.0, 10.0, delta=True)
     np.testing.assert_array_equal(bfd, fd)
     np.testing.assert_array_equal(bfa, fa)
+
+
+def test_half_millimetre_rounding(hc):
+    """Rule R1: every elevation sits on (or one float next to) a half millimetre, where
+    GRASS's (int)(z * 1000 +- 0.5) in double decides between two integers.  The doubled grid
+    keeps the DEM conditioned whichever way a cell rounds, so every direction code and count
+    below depends on the exact integers."""
+    base = oracle.synth_dem(21, 300, 420)
+    zi = np.rint(base.astype(np.float64) * 1000.0).astype(np.int64)
+    rng = np.random.default_rng(5)
+    for sign in (1.0, -1.0):
+        z = ((2 * zi + 0.5) / 1000.0).astype(np.float32)
+        nudge = rng.integers(-1, 2, z.shape)
+        z = np.where(nudge < 0, np.nextafter(z, np.float32(-1e9)),
+                     np.where(nudge > 0, np.nextafter(z, np.float32(1e9)), z)).astype(np.float32)
+        if sign < 0:  # negative elevations round away from zero as well
+            z = (z - np.float32(2.0 * (zi.max() + 10) / 1000.0)).astype(np.float32)
+            assert (z < 0).all()
+        assert oracle.check_conditioned(z) == (0, 0)
+        check_fd_fa(hc, z, None, 10.0, 10.0)
