@@ -544,20 +544,77 @@ __device__ __forceinline__ void smem_add64(uint32_t *lo, uint32_t *hi, long long
         atomicAdd(hi, h);
 }
 
-constexpr int SMW_PTR = SM_EFF;                  // uint16[T*T] pointer entries
-constexpr int SMW_LO = SMW_PTR + T * T * 2;      // uint32[T*T] low words of the sums
+constexpr int SMW_PTR = SM_EFF;                  // uint32[T*T] pointer entries (shared addresses | active)
+constexpr int SMW_LO = SMW_PTR + T * T * 4;      // uint32[T*T] low words of the sums
 constexpr int SMW_HI = SMW_LO + T * T * 4;       // uint32[T*T] high words
-constexpr int SMW_LUT = SMW_HI + T * T * 4;      // uint32[16] code -> pointer step | active
-constexpr int SMW_BAR = SMW_LUT + 64;            // mbarrier, counters, tile maximum
+constexpr int SMW_LUT = SMW_HI + T * T * 4;      // uint32[2][16] code -> pointer step | active (as stored, transposed)
+constexpr int SMW_BAR = SMW_LUT + 128;           // mbarrier, counters, tile maximum
 constexpr int SMW_TOTAL = SMW_BAR + 32;
+constexpr int W_DLO = SMW_LO - SMW_PTR, W_DHI = SMW_HI - SMW_PTR;
+
+// The rounds of the weighted kernel, branch-free on 32-bit shared addresses like the count
+// kernel's.  A 64-bit hand-off is a returning add of the low word (the carry needs the old
+// value) and a fire-and-forget add of the high word; the returning adds of a GROUP of cells
+// are issued back to back, their carries are resolved afterwards, so that the latencies of
+// the atomics overlap instead of adding up.
+__device__ __forceinline__ unsigned w_add_lo(unsigned low, unsigned alo)
+{
+    unsigned old;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, f;\n"
+        "and.b32 f, %1, 1;\n"
+        "setp.ne.u32 p, f, 0;\n"
+        "and.b32 t, %1, 0xFFFFFFFC;\n"
+        "mov.b32 %0, 0;\n"
+        "@p atom.shared.add.u32 %0, [t + %3], %2;\n"
+        "}\n"
+        : "=r"(old)
+        : "r"(low), "r"(alo), "n"(W_DLO)
+        : "memory");
+    return old;
+}
+// carry of the low add into the high word, then the target's entry (active cells only)
+__device__ __forceinline__ void w_add_hi(unsigned &low, unsigned old, unsigned alo, unsigned ahi)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 t, f, s, h;\n"
+        "and.b32 f, %0, 1;\n"
+        "setp.ne.u32 p, f, 0;\n"
+        "and.b32 t, %0, 0xFFFFFFFC;\n"
+        "add.u32 s, %1, %2;\n"
+        "setp.lt.u32 q, s, %1;\n"
+        "selp.u32 h, 1, 0, q;\n"
+        "add.u32 h, h, %3;\n"
+        "setp.ne.and.u32 q, h, 0, p;\n"
+        "@q red.shared.add.u32 [t + %4], h;\n"
+        "@p ld.shared.u32 %0, [t];\n"
+        "}\n"
+        : "+r"(low)
+        : "r"(old), "r"(alo), "r"(ahi), "n"(W_DHI)
+        : "memory");
+}
+// publish the new entry, snapshot the own sums
+__device__ __forceinline__ void w_publish(unsigned own_addr, unsigned low, unsigned &alo, unsigned &ahi)
+{
+    asm volatile(
+        "st.shared.u32 [%2], %3;\n"
+        "ld.shared.u32 %0, [%2 + %4];\n"
+        "ld.shared.u32 %1, [%2 + %5];\n"
+        : "=r"(alo), "=r"(ahi)
+        : "r"(own_addr), "r"(low), "n"(W_DLO), "n"(W_DHI)
+        : "memory");
+}
 
 __global__ void __launch_bounds__(THREADS, 4)
 acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *pk = smem_raw;
-    unsigned char *ptrb = smem_raw + SMW_PTR;
-    uint16_t *ptr16 = reinterpret_cast<uint16_t *>(ptrb);
+    uint32_t *ptr32 = reinterpret_cast<uint32_t *>(smem_raw + SMW_PTR);
     uint32_t *alo = reinterpret_cast<uint32_t *>(smem_raw + SMW_LO);
     uint32_t *ahi = reinterpret_cast<uint32_t *>(smem_raw + SMW_HI);
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw + SMW_LUT);
@@ -565,6 +622,7 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     int *ctl = reinterpret_cast<int *>(smem_raw + SMW_BAR + 8); // [0] entries, [1] their place in the list
     unsigned *tmaxb = reinterpret_cast<unsigned *>(smem_raw + SMW_BAR + 16);
     unsigned *tminb = reinterpret_cast<unsigned *>(smem_raw + SMW_BAR + 20);
+    int *vote = reinterpret_cast<int *>(smem_raw + SMW_BAR + 24);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -572,6 +630,7 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
     const int64_t x0 = (int64_t)tx * T, y0 = (int64_t)ty * T;
     if (tid == 0) {
         ctl[0] = 0;
+        *vote = 0;
         *tmaxb = 0u;
         *tminb = 0x7F800000u;
         ht::mbar_init(&bar, 1);
@@ -579,47 +638,82 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         ht::mbar_expect_tx(&bar, RH * RP);
         ht::tma_load_2d(pk, &map, (int)x0 - XO, (int)y0 - 1 + p.halo_top, &bar);
     }
-    if (tid < 16)
-        lut[tid] = link_offset_of(tid) ? (unsigned)(link_offset_of(tid) * 2) + J_ACTIVE : 0u;
+    if (tid < 32) {
+        const int code = tid & 15;
+        const int off = tid < 16 ? link_offset_of(code) : code_dc(code) * T + code_dr(code);
+        lut[tid] = link_offset_of(code) ? (unsigned)(off * 4) + J_ACTIVE : 0u;
+    }
     const int th = (int)min((int64_t)T, p.rows - y0), tw = (int)min((int64_t)T, p.cols - x0);
-    const int lx = tid & (T - 1), ly0 = tid >> 6;
-    // the thread's weights while the TMA is in flight
+    // array cell (u, v0 + 4k) of the thread: raster (row v, column u) as stored, (row u, column v)
+    // when the tile keeps its arrays transposed (see acc_local_cnt_kernel)
+    const int u = tid & (T - 1), v0 = tid >> 6;
+    const unsigned pbase = ht::smem_u32(ptr32), own0 = pbase + 4u * (unsigned)tid;
+    // the thread's weights in RASTER order (coalesced) while the TMA is in flight
     float wv[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; k++) {
-        const int ly = ly0 + 4 * k;
-        wv[k] = (lx < tw && ly < th) ? clean_weight(p.w[(y0 + ly) * p.w_ld + x0 + lx], p.has_wnd, p.wnd) : 0.0f;
+        const int ly = v0 + 4 * k;
+        wv[k] = (u < tw && ly < th) ? clean_weight(p.w[(y0 + ly) * p.w_ld + x0 + u], p.has_wnd, p.wnd) : 0.0f;
     }
     __syncthreads();
     ht::mbar_wait(&bar, 0);
 
-    unsigned low[CPT];
+    // ---- NULL cells weigh nothing; tile extremes; orientation vote
     {
-        const unsigned cm = (lx == 0 ? EX_W : 0u) | (lx == tw - 1 ? EX_E : 0u) | (lx >= tw ? 0xFFFFu : 0u) | 1u;
         float m = 0.0f, mn = __uint_as_float(0x7F800000u);
+        int score = 0;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            const int ly = ly0 + 4 * k;
-            const unsigned b = pk[(ly + 1) * RP + XO + lx];
-            const unsigned ex = cm | (ly == 0 ? EX_N : 0u) | (ly == th - 1 ? EX_S : 0u) | (ly >= th ? 0xFFFFu : 0u);
-            const unsigned code = b & HT_DIR_CODE;
-            const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
+            const int at = (v0 + 4 * k + 1) * RP + XO + u;
+            const unsigned b = pk[at];
             if (b & HT_DIR_NULL)
                 wv[k] = 0.0f;
             const float aw = fabsf(wv[k]);
             m = fmaxf(m, aw);
             mn = aw > 0.0f ? fminf(mn, aw) : mn;
-            low[k] = 2u * (unsigned)(tid + k * THREADS) + (stop ? 0u : lut[code]);
-            ptr16[tid + k * THREADS] = (uint16_t)low[k];
+            if ((k & 3) == 0) { // 4 sampled cells per thread, displacement over two steps
+                const int c1 = (int)(b & HT_DIR_CODE);
+                if (!(b & FLAGS_STOP) && c1) {
+                    int ddr = code_dr(c1), ddc = code_dc(c1);
+                    const unsigned b2 = pk[at + ddr * RP + ddc];
+                    const int c2 = (int)(b2 & HT_DIR_CODE);
+                    if (!(b2 & FLAGS_STOP) && c2) {
+                        ddr += code_dr(c2);
+                        ddc += code_dc(c2);
+                    }
+                    score += (abs(ddr) > abs(ddc)) - (abs(ddr) < abs(ddc));
+                }
+            }
         }
         const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
         const unsigned wn = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
-        if (lane == 0 && wm) {
-            atomicMax(tmaxb, wm);
-            atomicMin(tminb, wn);
+        score = __reduce_add_sync(0xffffffffu, score);
+        if (lane == 0) {
+            if (wm) {
+                atomicMax(tmaxb, wm);
+                atomicMin(tminb, wn);
+            }
+            if (score)
+                atomicAdd(vote, score);
         }
     }
     __syncthreads();
+    const bool tr = *vote > 0; // flow runs along the raster's columns: arrays transposed
+    const uint32_t *lutm = lut + (tr ? 16 : 0);
+    if (tr) {
+        // the weights were read in raster order: turn them through a padded staging block
+        // (pitch 65 words: both the row-wise writes and the column-wise reads are
+        // conflict-free) laid over the sum planes, which are not initialised yet
+        float *stage = reinterpret_cast<float *>(alo);
+#pragma unroll
+        for (int k = 0; k < CPT; k++)
+            stage[u * (T + 1) + v0 + 4 * k] = wv[k]; // raster (row v0 + 4k, column u)
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CPT; k++)
+            wv[k] = stage[(v0 + 4 * k) * (T + 1) + u]; // raster (row u, column v0 + 4k)
+        __syncthreads();
+    }
     // per-tile unit: fine enough that the tile's SMALLEST weight keeps Q_KEEP significant bits,
     // never coarser than what lets its largest weight fit Q_BITS bits, never finer than the
     // global unit; and not finer than needed -- sums below 2^32 units cost one shared atomic
@@ -633,56 +727,85 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         et = max(0, ilogbf(tmax) + 1 + sg - qbits);
     }
     const double sc = pow2d(sg - et);
-    long long a[CPT];
+
+    // ---- per cell: pointer entry and own value
+    unsigned low[CPT], slo[CPT], shi[CPT];
+    {
+        const int lim_u = tr ? th : tw, lim_v = tr ? tw : th;
+        const unsigned lo_u = tr ? EX_N : EX_W, hi_u = tr ? EX_S : EX_E;
+        const unsigned lo_v = tr ? EX_W : EX_N, hi_v = tr ? EX_E : EX_S;
+        const unsigned cm = (u == 0 ? lo_u : 0u) | (u == lim_u - 1 ? hi_u : 0u) | (u >= lim_u ? 0xFFFFu : 0u) | 1u;
+        unsigned bw[CPT];
+        if (tr) {
+            const uint4 *row = reinterpret_cast<const uint4 *>(pk + (u + 1) * RP + XO);
 #pragma unroll
-    for (int k = 0; k < CPT; k++) {
-        a[k] = __double2ll_rn((double)wv[k] * sc);
-        alo[tid + k * THREADS] = (uint32_t)a[k];
-        ahi[tid + k * THREADS] = (uint32_t)((unsigned long long)a[k] >> 32);
+            for (int q = 0; q < CPT / 4; q++) {
+                const uint4 w4 = row[q];
+                bw[4 * q] = w4.x; bw[4 * q + 1] = w4.y; bw[4 * q + 2] = w4.z; bw[4 * q + 3] = w4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; k++)
+                bw[k] = (bw[k] >> (8 * v0)) & 0xFFu;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; k++)
+                bw[k] = pk[(v0 + 1 + 4 * k) * RP + XO + u];
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int v = v0 + 4 * k;
+            const unsigned b = bw[k];
+            const unsigned ex = cm | (v == 0 ? lo_v : 0u) | (v == lim_v - 1 ? hi_v : 0u) | (v >= lim_v ? 0xFFFFu : 0u);
+            const unsigned code = b & HT_DIR_CODE;
+            const bool stop = (b & FLAGS_STOP) || ((ex >> code) & 1u);
+            const long long a = __double2ll_rn((double)wv[k] * sc);
+            slo[k] = (uint32_t)a;
+            shi[k] = (uint32_t)((unsigned long long)a >> 32);
+            low[k] = own0 + (unsigned)(k * THREADS * 4) + (stop ? 0u : lutm[code]);
+            ptr32[tid + k * THREADS] = low[k];
+            alo[tid + k * THREADS] = slo[k];
+            ahi[tid + k * THREADS] = shi[k];
+        }
     }
     __syncthreads();
 
-    // ---- pointer doubling (as in acc_local_cnt_kernel); the sums include the cell's own weight
+    // ---- pointer doubling; the sums include the cell's own weight
     for (int round = 0; round < MAX_ROUNDS; round++) {
-        unsigned was = 0;
 #pragma unroll
-        for (int k = 0; k < CPT; k++) {
-            if (low[k] & J_ACTIVE) {
-                const unsigned t2 = low[k] & J_PTR; // 2 * (cell 2^k steps downstream)
-                const unsigned wt = *reinterpret_cast<const uint16_t *>(ptrb + t2);
-                if (a[k])
-                    smem_add64(alo + (t2 >> 1), ahi + (t2 >> 1), a[k]);
-                low[k] = wt;
-                was |= 1u << k;
-            }
+        for (int g = 0; g < CPT; g += 8) {
+            unsigned old[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                old[k] = w_add_lo(low[g + k], slo[g + k]);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                w_add_hi(low[g + k], old[k], slo[g + k], shi[g + k]);
         }
         __syncthreads();
-        bool still = false;
+        unsigned any = 0;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            if ((was >> k) & 1u) {
-                ptr16[tid + k * THREADS] = (uint16_t)low[k];
-                if (low[k] & J_ACTIVE) {
-                    a[k] = (long long)(((unsigned long long)ahi[tid + k * THREADS] << 32) | alo[tid + k * THREADS]);
-                    still = true;
-                }
-            }
+            w_publish(own0 + (unsigned)(k * THREADS * 4), low[k], slo[k], shi[k]);
+            any |= low[k];
         }
-        if (!__syncthreads_or(still))
+        if (!__syncthreads_or((int)(any & J_ACTIVE)))
             break;
     }
 
     // ---- boundary graph.  thread -> one perimeter slot
+    long long exit_val = 0;
+    int32_t exit_to = 0;
     {
         int ly = 0, plx = 0;
         const bool per = perimeter_cell(tid, th, tw, ly, plx);
         const unsigned b = per ? pk[(ly + 1) * RP + plx + XO] : (unsigned)HT_DIR_NULL;
+        // flow that leaves the tile through this cell: read now, added to the boundary graph at
+        // the very end -- the 128-bit add is two dependent global atomics (the carry), and the
+        // barriers below would make the whole CTA wait for them
         if (per && leaves_tile(b, ly, plx, th, tw)) {
-            const long long val = (long long)(((unsigned long long)ahi[ly * T + plx] << 32) | alo[ly * T + plx]);
-            if (val)
-                atomic_add_v(reinterpret_cast<i128 *>(p.base) +
-                                 exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE)),
-                             shl_i64(val, et + W_MARK_BITS));
+            const int at = arr_index(tr, ly, plx);
+            exit_val = (long long)(((unsigned long long)ahi[at] << 32) | alo[at]);
+            exit_to = exit_slot(p, tx, ty, ly, plx, (int)(b & HT_DIR_CODE));
         }
         bool entry = false;
         if (per && !(b & HT_DIR_NULL)) {
@@ -694,8 +817,8 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
                 const int ny = yy + kk / 3 - 1, nx = xx + kk % 3 - 1;
                 if (ny >= 1 && ny <= th && nx >= XO && nx < XO + tw)
                     continue; // inside the tile
-                const unsigned u = pk[ny * RP + nx]; // outside the raster: TMA filled 0
-                entry |= !(u & FLAGS_STOP) && (u & HT_DIR_CODE) == (unsigned)win2code(8 - kk);
+                const unsigned w = pk[ny * RP + nx]; // outside the raster: TMA filled 0
+                entry |= !(w & FLAGS_STOP) && (w & HT_DIR_CODE) == (unsigned)win2code(8 - kk);
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, entry);
@@ -708,7 +831,8 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             ctl[1] = atomicAdd(p.nlist, ctl[0]);
         __syncthreads();
         if (entry) {
-            const int rc = (int)(ptr16[ly * T + plx] >> 1), cy = rc >> 6, cx = rc & (T - 1);
+            const int rc = (int)(((ptr32[arr_index(tr, ly, plx)] & ~3u) - pbase) >> 2);
+            const int cy = tr ? (rc & (T - 1)) : (rc >> 6), cx = tr ? (rc >> 6) : (rc & (T - 1));
             const unsigned rb = pk[(cy + 1) * RP + cx + XO];
             const int32_t slot = tile * SLOTS + tid;
             p.list[ctl[1] + at] = slot;
@@ -718,23 +842,44 @@ acc_local_w_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
         }
     }
 
-    // ---- tile-local sums (tile unit) and the tile's unit for stage C
+    // ---- tile-local sums (tile unit) and the tile's unit for stage C.  slo / shi hold them:
+    // the last snapshot was taken after the last hand-off.
     if (tid == 0)
         p.tile_e[tile] = et;
-    if (lx < tw) {
-        long long *dst = p.lacc64 + (y0 + ly0) * p.lacc64_ld + x0 + lx;
+    if (tr) {
+        // transposed arrays: back to raster order through a padded 64-bit staging block laid
+        // over the entries and the sum planes (everybody is done with them after the barrier)
+        __syncthreads();
+        unsigned long long *stage = reinterpret_cast<unsigned long long *>(ptr32);
+#pragma unroll
+        for (int k = 0; k < CPT; k++)
+            stage[u * (T + 1) + v0 + 4 * k] = ((unsigned long long)shi[k] << 32) | slo[k]; // (row u, column v)
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const unsigned long long v = stage[(v0 + 4 * k) * (T + 1) + u];
+            slo[k] = (uint32_t)v;
+            shi[k] = (uint32_t)(v >> 32);
+        }
+    }
+    if (u < tw) {
+        long long *dst = p.lacc64 + (y0 + v0) * p.lacc64_ld + x0 + u;
         const int64_t step = 4 * p.lacc64_ld;
 #pragma unroll
         for (int k = 0; k < CPT; k++, dst += step)
-            if (ly0 + 4 * k < th)
-                *dst = (long long)(((unsigned long long)ahi[tid + k * THREADS] << 32) | alo[tid + k * THREADS]);
+            if (v0 + 4 * k < th)
+                *dst = (long long)(((unsigned long long)shi[k] << 32) | slo[k]);
     }
+    if (exit_val)
+        atomic_add_v(reinterpret_cast<i128 *>(p.base) + exit_to, shl_i64(exit_val, et + W_MARK_BITS));
 }
 
 // stage C, weighted: final = tile-local sum (shifted to the global unit) + the resolved
 // inflow of every entry upstream, added along the entry's path by a walker.  Cells are
 // four 32-bit word planes in shared memory (128-bit integers, native 32-bit atomic adds
-// with the carry handed on).
+// with the carry handed on).  Measured and rejected: five planes of 24-bit limbs that never
+// carry (fire-and-forget REDs, the walk bound by one byte load per step) -- 95 KB per CTA
+// leave two CTAs per SM instead of three, 1.45 ms against 1.09.
 constexpr int WP = T + 4;                       // plane row pitch in words (see CP below)
 constexpr int SMX_W = T * T;                    // after the 64 x 64 packed tile
 constexpr int SMX_BAR = SMX_W + 4 * T * WP * 4;
