@@ -166,6 +166,8 @@ def workload_config(n):
         "rows": ROWS_PER_GPU * n, "cols": COLS, "seed": SEED, "cell_size_m": CSX,
         "sharding": "whole raster on one GPU" if n == 1 else f"{n} row bands of {ROWS_PER_GPU} rows",
         "l2": "inputs (400 MB DEM per GPU) exceed the 126 MB L2; no flush between iterations",
+        "step": "every kernel, memset and collective of BandEngine.flow_direction_accumulation, "
+                "captured once (after the warm-up) and replayed as one CUDA graph launch per step",
     }
 
 
@@ -525,7 +527,15 @@ def run_product(args):
     # One step = every kernel, memset and collective of engine.flow_direction_accumulation(),
     # captured once and replayed as ONE CUDA graph launch per step (BandEngine.graph): a
     # sharded step is ~40 host calls, and 8 ranks share the box's host cores.
-    step = engine.graph(engine.flow_direction_accumulation)
+    try:
+        step = engine.graph(engine.flow_direction_accumulation)
+        step_mode = "cuda graph replay (one launch per step)"
+    except Exception as exc:  # capture refused on this driver / NCCL: enqueue launch by launch
+        print(f"[bench] graph capture failed ({type(exc).__name__}: {exc}); launching step by step",
+              file=sys.stderr)
+        step = engine.flow_direction_accumulation
+        step.release = lambda: None
+        step_mode = "launch by launch"
     for _ in range(args.warmup):
         step()
     launches0 = engine.launches

@@ -17,7 +17,7 @@ if [[ " $* " == *" noprof "* ]]; then exit 0; fi
 # launch list of the bench command (per-launch times are cold-cache: compare shares)
 python bench.py --steps 2 --warmup 1 > $out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
-    -k regex:'d8_kernel|acc_|coarse_resolve|marked_nodes|band_|mark_edges|add_imports|weight_max|terrain_kernel|filter_kernel|row_prefix|alt_kernel|fill_|classify_|collect_|ccl_|generation_|quorum_|round_kernel|finish_kernel|deflate_|tile_|pack_i8|synth_' \
+    -k regex:'d8_kernel|acc_|coarse_resolve|marked_nodes|band_|mark_edges|add_imports|weight_max|terrain_kernel|filter_kernel|run_filter|row_prefix|tile_phase|alt_kernel|fill_|classify_|collect_|ccl_|generation_|quorum_|round_kernel|finish_kernel|deflate_|tile_|pack_i8|synth_' \
     --log-file $out/launches_$tag.csv python bench.py --steps 2 --warmup 1 > $out/ncu_bench_$tag.log 2>&1
 echo "launch list rc=$?"
 # full capture: the four kernels of one D8 + accumulation step (second step: warm)
