@@ -20,6 +20,7 @@
 //     exact integers for counts) and the final GRASS direction codes.
 // Counts are carried as u64 across tiles; weighted sums as fp64.
 // Algorithmic traffic: 1 B/cell read + 8 B/cell written (+4 B/cell weights).
+#include <cstdlib>
 #include <type_traits>
 
 #include "ht_common.cuh"
@@ -68,6 +69,8 @@ struct AccArgs {
     int64_t lacc64_ld;
     int32_t *tile_e;          // weighted mode: log2(tile unit / global unit) per tile
     const unsigned *gmax_bits; // weighted mode: bits of the raster's largest |weight| (float)
+    int32_t *tile_first;      // count modes: where the tile's entries start in `list`, and how
+    int32_t *tile_cnt;        // many they are (stage A out, for the two-level stage B)
     const uint8_t *tile_phase; // stage C of a sharded run: 1 = the tile's inflow depends on the
     int phase;                 // neighbour bands' deliveries; only tiles of `phase` are processed
 };
@@ -420,8 +423,14 @@ acc_local_cnt_kernel(const __grid_constant__ CUtensorMap map, const AccArgs p)
             at = atomicAdd(&ctl[0], __popc(m));
         at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
         __syncthreads();
-        if (tid == 0 && ctl[0])
-            ctl[1] = atomicAdd(p.nlist, ctl[0]);
+        if (tid == 0) {
+            if (ctl[0])
+                ctl[1] = atomicAdd(p.nlist, ctl[0]);
+            if (p.tile_cnt) {
+                p.tile_first[tile] = ctl[0] ? ctl[1] : 0;
+                p.tile_cnt[tile] = ctl[0];
+            }
+        }
         __syncthreads();
         if (entry) {
             // where the path that enters here leaves the tile: the root of the cell
@@ -1391,6 +1400,298 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
         *rounds_out = round + 1;
 }
 
+// ---------------------------------------------------------------------------
+// stage B in TWO LEVELS (count modes).  The flat resolve above touches every node of the
+// boundary graph in every round, from L2 / DRAM: 2.2 M nodes x 10 rounds for 10 000^2.
+// Super-tiles of SG x SG tiles cut the graph: links between tiles of one super-tile are
+// INTERNAL, the others EXTERNAL, a node with an external in-link is OUTER.
+//   K1  super_tile_kernel<1>: one CTA per super-tile resolves the internal forest in SHARED
+//       memory (the rounds of stage A on <= 16 K nodes): S1 = subtree sums over internal
+//       links, root1 = last node of the internal path.  A root with an external link hands
+//       S1 to its target (base2) and flags it OUTER; next2[v] = next0[root1(v)].
+//   K2  the flat resolve on the OUTER nodes only (~8x fewer): X = what arrives from other
+//       super-tiles, in total.
+//   K3  super_tile_kernel<3>: every OUTER node adds its X along its internal path (a walk of
+//       a few nodes): inflow = S1 + the X of the outer nodes upstream.
+// Inside a super-tile a sum of genuine tile-to-tile flows is below 2^19 cells: K1 works on
+// 32-bit words (native shared atomics); nodes with a large own value or a band-edge mark
+// are promoted to the X side.  K3 adds 64-bit values as two words with the carry handed
+// on.  Exact, so the result equals the flat resolve bit for bit.
+// ---------------------------------------------------------------------------
+constexpr int SG = 8;                       // tiles per super-tile edge
+constexpr int SUP_THREADS = 1024;
+constexpr int SUP_CPT = 16;                 // nodes per thread
+constexpr int SUP_MAXN = SG * SG * SLOTS;   // 16 384 = SUP_THREADS * SUP_CPT
+constexpr int S1_BIG_BITS = 20;             // own values from 2^20 on (and marked ones) go the X way
+static_assert(SUP_MAXN == SUP_THREADS * SUP_CPT, "one pass over a full super-tile");
+
+struct SupArgs {
+    int tiles_x, tiles_y, sup_x;
+    int32_t ntile_slots;
+    const int32_t *list, *next0, *tile_first, *tile_cnt;
+    int32_t *idmap;
+    const unsigned long long *base0;
+    uint8_t *outer;
+    unsigned long long *base2;
+    int32_t *next2;
+    uint32_t *s1w;
+    unsigned long long *agg;     // K3: X of the outer nodes in, inflow of every node out
+    int32_t *root1;              // K1, row bands: last node of the internal path, band-edge slots only
+    int edge_tiles_x, edge_tiles_y, edge_last_h;
+};
+
+constexpr int SUP_SM_PTR = 0;                        // K1 pointer entries / K3 next node
+constexpr int SUP_SM_V0 = SUP_SM_PTR + SUP_MAXN * 4; // K1 packed sums / K3 low words
+constexpr int SUP_SM_V1 = SUP_SM_V0 + SUP_MAXN * 4;  // K3 high words
+constexpr int SUP_SM_TAB = SUP_SM_V1 + SUP_MAXN * 4; // int[65] prefix, int[64] first
+constexpr int SUP_SM_TOTAL = SUP_SM_TAB + 130 * 4;
+
+// K1's rounds: cnt_hand_on / cnt_publish with this kernel's delta between entry and sum
+__device__ __forceinline__ void sup_hand_on(unsigned &low, unsigned a)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, f;\n"
+        "and.b32 f, %0, 1;\n"
+        "setp.ne.u32 p, f, 0;\n"
+        "and.b32 t, %0, 0xFFFFFFFC;\n"
+        "@p red.shared.add.u32 [t + %2], %1;\n"
+        "@p ld.shared.u32 %0, [t];\n"
+        "}\n"
+        : "+r"(low)
+        : "r"(a), "n"(SUP_SM_V0 - SUP_SM_PTR)
+        : "memory");
+}
+__device__ __forceinline__ unsigned sup_publish(unsigned own_addr, unsigned low)
+{
+    unsigned a;
+    asm volatile(
+        "st.shared.u32 [%1], %2;\n"
+        "ld.shared.u32 %0, [%1 + %3];\n"
+        : "=r"(a)
+        : "r"(own_addr), "r"(low), "n"(SUP_SM_V0 - SUP_SM_PTR)
+        : "memory");
+    return a;
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(SUP_THREADS, 1)
+super_tile_kernel(const SupArgs p)
+{
+    extern __shared__ __align__(16) unsigned char sup_sm[];
+    uint32_t *sptr = reinterpret_cast<uint32_t *>(sup_sm + SUP_SM_PTR);
+    uint32_t *sv0 = reinterpret_cast<uint32_t *>(sup_sm + SUP_SM_V0);
+    uint32_t *sv1 = reinterpret_cast<uint32_t *>(sup_sm + SUP_SM_V1);
+    int *tpre = reinterpret_cast<int *>(sup_sm + SUP_SM_TAB); // [65]
+    int *tfirst = tpre + 65;                                   // [64]
+    const int tid = threadIdx.x;
+    const int gx = blockIdx.x % p.sup_x, gy = blockIdx.x / p.sup_x;
+
+    // ---- the super-tile's tiles and their entries in the node list
+    if (tid < SG * SG) {
+        const int ty = gy * SG + tid / SG, tx = gx * SG + tid % SG;
+        int cnt = 0, first = 0;
+        if (ty < p.tiles_y && tx < p.tiles_x) {
+            const int t = ty * p.tiles_x + tx;
+            cnt = p.tile_cnt[t];
+            first = p.tile_first[t];
+        }
+        tfirst[tid] = first;
+        tpre[tid + 1] = cnt; // turned into a prefix below
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        tpre[0] = 0;
+        for (int j = 1; j <= SG * SG; j++) {
+            run += tpre[j];
+            tpre[j] = run;
+        }
+    }
+    __syncthreads();
+    const int nG = tpre[SG * SG];
+    if (nG == 0)
+        return;
+    auto slot_of_index = [&](int i) -> int32_t {
+        int lo = 0, hi = SG * SG; // largest j with tpre[j] <= i
+#pragma unroll
+        for (int it = 0; it < 6; it++) {
+            const int mid = (lo + hi) >> 1;
+            if (tpre[mid] <= i)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return p.list[tfirst[lo] + (i - tpre[lo])];
+    };
+    auto internal = [&](int32_t nx) -> bool {
+        if (nx < 0 || nx >= p.ntile_slots)
+            return false;
+        const int tile = nx / SLOTS, ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        return ty / SG == gy && tx / SG == gx;
+    };
+
+    int32_t slot[SUP_CPT];
+#pragma unroll
+    for (int k = 0; k < SUP_CPT; k++) {
+        const int i = tid + k * SUP_THREADS;
+        slot[k] = i < nG ? slot_of_index(i) : -1;
+        if (PHASE == 1 && i < nG)
+            p.idmap[slot[k]] = i;
+    }
+    __syncthreads(); // idmap of this super-tile's nodes is read by this CTA only
+
+    const unsigned pbase = ht::smem_u32(sptr), own0 = pbase + 4u * (unsigned)tid;
+    if (PHASE == 1) {
+        unsigned low[SUP_CPT], a[SUP_CPT];
+#pragma unroll
+        for (int k = 0; k < SUP_CPT; k++) {
+            const int i = tid + k * SUP_THREADS;
+            low[k] = own0 + (unsigned)(k * SUP_THREADS * 4);
+            a[k] = 0u;
+            if (i < nG) {
+                const int32_t nx = p.next0[slot[k]];
+                if (internal(nx))
+                    low[k] = (pbase + 4u * (unsigned)p.idmap[nx]) | J_ACTIVE;
+                // a node whose own value is large (flow imported from a neighbour band) or
+                // carries a band-edge mark is PROMOTED: its value joins what arrives from
+                // outside (base2 -> X, exact by linearity), so that K1's sums stay plain
+                // 32-bit counts: <= 2^19 cells of the super-tile and its ring, + 2^10 band-edge
+                // nodes x 2^20
+                const unsigned long long b = p.base0[slot[k]];
+                if (b >= (1ull << S1_BIG_BITS)) {
+                    atomicAdd(p.base2 + slot[k], b);
+                    p.outer[slot[k]] = 1;
+                } else
+                    a[k] = (unsigned)b;
+            }
+            sptr[i] = low[k];
+            sv0[i] = a[k];
+        }
+        __syncthreads();
+        for (int round = 0; round < 16; round++) {
+#pragma unroll
+            for (int k = 0; k < SUP_CPT; k++)
+                sup_hand_on(low[k], a[k]);
+            __syncthreads();
+            unsigned any = 0;
+#pragma unroll
+            for (int k = 0; k < SUP_CPT; k++) {
+                a[k] = sup_publish(own0 + (unsigned)(k * SUP_THREADS * 4), low[k]);
+                any |= low[k];
+            }
+            if (!__syncthreads_or((int)(any & J_ACTIVE)))
+                break;
+        }
+        // a[] = S1 (packed), low[] = the root of the internal path
+#pragma unroll
+        for (int k = 0; k < SUP_CPT; k++) {
+            const int i = tid + k * SUP_THREADS;
+            if (i >= nG)
+                continue;
+            const int ri = (int)(((low[k] & ~3u) - pbase) >> 2);
+            const int32_t rslot = ri == i ? slot[k] : slot_of_index(ri);
+            const int32_t nxr = p.next0[rslot];
+            p.s1w[slot[k]] = a[k];
+            p.next2[slot[k]] = nxr;
+            if (ri == i && nxr >= 0) {
+                // the end of an internal path with a link out of the super-tile
+                if (a[k])
+                    atomicAdd(p.base2 + nxr, (unsigned long long)a[k]);
+                p.outer[nxr] = 1;
+            }
+            if (p.root1 && is_band_edge_slot(slot[k], p.edge_tiles_x, p.edge_tiles_y, p.edge_last_h))
+                p.root1[slot[k]] = rslot;
+        }
+    } else {
+        // ---- K3: one-hop internal links, S1 as 64-bit words, the outer nodes walk their X down
+        int32_t *snext = reinterpret_cast<int32_t *>(sptr);
+#pragma unroll
+        for (int k = 0; k < SUP_CPT; k++) {
+            const int i = tid + k * SUP_THREADS;
+            if (i >= nG)
+                continue;
+            const int32_t nx = p.next0[slot[k]];
+            snext[i] = internal(nx) ? p.idmap[nx] : -1;
+            sv0[i] = p.s1w[slot[k]];
+            sv1[i] = 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SUP_CPT; k++) {
+            const int i = tid + k * SUP_THREADS;
+            if (i >= nG || !p.outer[slot[k]])
+                continue;
+            const unsigned long long x = p.agg[slot[k]];
+            if (!x)
+                continue;
+            for (int cur = i, step = 0; cur >= 0 && step < SUP_MAXN; cur = snext[cur], step++)
+                smem_add64(sv0 + cur, sv1 + cur, (long long)x);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SUP_CPT; k++) {
+            const int i = tid + k * SUP_THREADS;
+            if (i < nG)
+                p.agg[slot[k]] = ((unsigned long long)sv1[i] << 32) | sv0[i];
+        }
+    }
+}
+
+// the cells of the neighbour bands (virtual slots) belong to no tile: stage A adds what the
+// band's edge rows hand them to their base0 directly; they are level-2 nodes with that value
+__global__ void virtual_nodes_kernel(const unsigned long long *base0, unsigned long long *base2,
+                                     uint8_t *outer, int64_t first, int64_t count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    const unsigned long long b = base0[first + i];
+    if (b) {
+        base2[first + i] += b;
+        outer[first + i] = 1;
+    }
+}
+
+// the OUTER nodes of the node list, for the level-2 resolve
+__global__ void outer_nodes_kernel(const uint8_t *outer, const int32_t *list, const int *nlist,
+                                   int32_t *list2, int *nlist2)
+{
+    const int na = *nlist;
+    const int lane = threadIdx.x & 31;
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < na; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        const int32_t u = i < na ? list[i] : 0;
+        const bool in = i < na && outer[u];
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (!m)
+            continue;
+        int at = 0;
+        if (lane == 0)
+            at = atomicAdd(nlist2, __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+        if (in)
+            list2[at] = u;
+    }
+}
+
+// row bands: the last node of the path of every slot of the band's first / last row --
+// root1 (K1) if the internal path ends inside its super-tile, else the level-2 root of the
+// outer node that path hands over to
+__global__ void edge_roots_kernel(int32_t *root_out, const int32_t *root1, const int32_t *next2,
+                                  const int32_t *rootX, int tiles_x, int tiles_y, int last_h)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 2ll * tiles_x * T)
+        return;
+    const int side = c >= (int64_t)tiles_x * T, cc = (int)(c - (int64_t)side * tiles_x * T);
+    const int32_t s = band_edge_slot_of(side, cc / T, cc % T, tiles_x, tiles_y, last_h);
+    const int32_t n2 = next2[s];              // -1: not a node, or its path ends in its super-tile
+    const int32_t r1 = root1[s];              // -1: not a node
+    root_out[s] = n2 >= 0 ? rootX[n2] : (r1 >= 0 ? r1 : s);
+}
+
 __global__ void append_range_kernel(int32_t *list, int *nlist, int32_t first, int32_t count)
 {
     __shared__ int base;
@@ -1624,6 +1925,10 @@ struct Workspace {
     int *nlist2;
     int *flags, *nlist;
     unsigned *gmax_bits;
+    // two-level stage B (count modes)
+    int32_t *tile_first, *tile_cnt, *next2, *idmapX, *rootX, *root1;
+    uint32_t *s1w;
+    uint8_t *outer;
     int64_t nslots;
     int vsize; // bytes per boundary-graph value: 8 (u64 counts) or 16 (i128 weighted sums)
 };
@@ -1647,7 +1952,11 @@ size_t workspace_bytes(int64_t rows, int64_t cols, int mode)
                 align_up((size_t)ht::cdiv(rows, T) * ht::cdiv(cols, T) * 4);
     else
         local = align_up((size_t)rows * ((cols + 7) / 8 * 8) * 2);
-    return 6 * align_up(n * vs) + 9 * align_up(n * 4) + align_up(128 * sizeof(int)) + local + 256;
+    size_t hier = 0;
+    if (mode != W_F32)
+        hier = 5 * align_up(n * 4) + align_up(n) +
+               2 * align_up((size_t)ht::cdiv(rows, T) * ht::cdiv(cols, T) * 4);
+    return 6 * align_up(n * vs) + 9 * align_up(n * 4) + align_up(128 * sizeof(int)) + local + hier + 256;
 }
 
 int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, int mode, Workspace &w)
@@ -1686,6 +1995,20 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, int mode, Works
     else {
         w.lacc = (uint16_t *)b;
         w.lacc_ld = (cols + 7) / 8 * 8;
+        b += align_up((size_t)rows * w.lacc_ld * 2);
+    }
+    w.tile_first = w.tile_cnt = w.next2 = w.idmapX = w.rootX = w.root1 = nullptr;
+    w.s1w = nullptr; w.outer = nullptr;
+    if (mode != W_F32) {
+        const size_t nt = (size_t)ht::cdiv(rows, T) * ht::cdiv(cols, T);
+        w.next2 = (int32_t *)b; b += align_up(n * 4);
+        w.idmapX = (int32_t *)b; b += align_up(n * 4);
+        w.rootX = (int32_t *)b; b += align_up(n * 4);
+        w.root1 = (int32_t *)b; b += align_up(n * 4);
+        w.s1w = (uint32_t *)b; b += align_up(n * 4);
+        w.outer = (uint8_t *)b; b += align_up(n);
+        w.tile_first = (int32_t *)b; b += align_up(nt * 4);
+        w.tile_cnt = (int32_t *)b; b += align_up(nt * 4);
     }
     w.nslots = n;
     w.vsize = (int)vs;
@@ -1782,6 +2105,71 @@ int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int
     return 0;
 }
 
+// HT_STAGE_B = flat | two forces one variant of stage B (tests); default: two levels from
+// one full super-tile on
+int stage_b_choice()
+{
+    static int choice = -1;
+    if (choice < 0) {
+        const char *e = getenv("HT_STAGE_B");
+        choice = !e ? 0 : (e[0] == 'f' ? 1 : (e[0] == 't' ? 2 : 0));
+    }
+    return choice;
+}
+
+int resolve_two_level(Workspace &wk, int64_t rows, int64_t cols, int want_roots, int *rounds_dev,
+                      cudaStream_t st)
+{
+    const int tiles_x = ht::cdiv(cols, T), tiles_y = ht::cdiv(rows, T);
+    const int sup_x = ht::cdiv(tiles_x, SG), sup_y = ht::cdiv(tiles_y, SG);
+    const int last_h = (int)(rows - (int64_t)(tiles_y - 1) * T);
+    HT_CUDA_TRY(cudaMemsetAsync(wk.outer, 0, wk.nslots, st));
+    HT_CUDA_TRY(cudaMemsetAsync(wk.base2, 0, wk.nslots * 8, st));
+    HT_CUDA_TRY(cudaMemsetAsync(wk.next2, 0xFF, wk.nslots * 4, st));
+    if (want_roots)
+        HT_CUDA_TRY(cudaMemsetAsync(wk.root1, 0xFF, wk.nslots * 4, st));
+    SupArgs a;
+    a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.sup_x = sup_x;
+    a.ntile_slots = tiles_x * tiles_y * SLOTS;
+    a.list = wk.list; a.next0 = wk.next0; a.tile_first = wk.tile_first; a.tile_cnt = wk.tile_cnt;
+    a.idmap = wk.idmap;
+    a.base0 = (const unsigned long long *)wk.base0;
+    a.outer = wk.outer;
+    a.base2 = (unsigned long long *)wk.base2;
+    a.next2 = wk.next2; a.s1w = wk.s1w;
+    a.agg = (unsigned long long *)wk.aggB;
+    a.root1 = want_roots ? wk.root1 : nullptr;
+    a.edge_tiles_x = tiles_x; a.edge_tiles_y = tiles_y; a.edge_last_h = last_h;
+    HT_CUDA_TRY(cudaFuncSetAttribute(super_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SUP_SM_TOTAL));
+    HT_CUDA_TRY(cudaFuncSetAttribute(super_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SUP_SM_TOTAL));
+    super_tile_kernel<1><<<sup_x * sup_y, SUP_THREADS, SUP_SM_TOTAL, st>>>(a);
+    HT_LAUNCH_CHECK();
+    {
+        const int64_t nv = wk.nslots - (int64_t)a.ntile_slots; // 2 * cols
+        virtual_nodes_kernel<<<ht::cdiv(nv, 256), 256, 0, st>>>((const unsigned long long *)wk.base0,
+                                                               (unsigned long long *)wk.base2, wk.outer,
+                                                               (int64_t)a.ntile_slots, nv);
+        HT_LAUNCH_CHECK();
+    }
+    HT_CUDA_TRY(cudaMemsetAsync(wk.nlist2, 0, sizeof(int), st));
+    outer_nodes_kernel<<<ht::kSMs * 4, 256, 0, st>>>(wk.outer, wk.list, wk.nlist, wk.list2, wk.nlist2);
+    HT_LAUNCH_CHECK();
+    int rc = launch_resolve<unsigned long long>(wk.base2, wk.next2, wk.nslots, wk.list2, wk.nlist2, wk.idmapX,
+                                                wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
+                                                want_roots ? wk.rootA : nullptr, want_roots ? wk.rootC : nullptr,
+                                                wk.aggB, want_roots ? wk.rootX : nullptr, wk.flags, rounds_dev, st);
+    if (rc)
+        return rc;
+    super_tile_kernel<3><<<sup_x * sup_y, SUP_THREADS, SUP_SM_TOTAL, st>>>(a);
+    HT_LAUNCH_CHECK();
+    if (want_roots) {
+        edge_roots_kernel<<<ht::cdiv(2ll * tiles_x * T, 256), 256, 0, st>>>(wk.rootB, wk.root1, wk.next2, wk.rootX,
+                                                                          tiles_x, tiles_y, last_h);
+        HT_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t total_rows,
               int halo_top, int halo_bot)
 {
@@ -1799,6 +2187,7 @@ int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t tota
     p.list = nullptr; p.nlist = nullptr;
     p.lacc64 = nullptr; p.lacc64_ld = 0; p.tile_e = nullptr; p.gmax_bits = nullptr;
     p.tile_phase = nullptr; p.phase = 0;
+    p.tile_first = nullptr; p.tile_cnt = nullptr;
     return 0;
 }
 
@@ -1882,6 +2271,7 @@ extern "C" int ht_acc_local(const uint8_t *packed, int64_t packed_ld, int64_t ro
     p.lacc64 = wk.lacc64; p.lacc64_ld = wk.lacc64_ld; p.tile_e = wk.tile_e; p.gmax_bits = wk.gmax_bits;
     p.packed = packed; p.packed_ld = packed_ld;
     p.list = wk.list; p.nlist = wk.nlist;
+    p.tile_first = wk.tile_first; p.tile_cnt = wk.tile_cnt;
     HT_CUDA_TRY(cudaMemsetAsync(wk.nlist, 0, sizeof(int), st));
     if ((rc = dispatch_tile<false>(mode, map, p, st)))
         return rc;
@@ -1914,6 +2304,12 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
     // the last node of a path is only ever asked for at the slots of the band's first / last row
     const int etx = want_roots ? ht::cdiv(cols, T) : 0, ety = ht::cdiv(rows, T);
     const int elh = (int)(rows - (int64_t)(ety - 1) * T);
+    if (mode != W_F32) {
+        const int choice = stage_b_choice();
+        const int64_t ntiles = (int64_t)ht::cdiv(cols, T) * ety;
+        if (choice == 2 || (choice == 0 && ntiles >= SG * SG))
+            return resolve_two_level(wk, rows, cols, want_roots, rounds_dev, (cudaStream_t)stream);
+    }
     if (mode == W_F32)
         return launch_resolve<i128>(wk.base0, wk.next0, wk.nslots, wk.list, wk.nlist, wk.idmap,
                                     wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1, rA, rC, wk.aggB,
