@@ -691,8 +691,8 @@ def run_product(args):
                 "peak_kind": f"of {peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic,
                 "share_of_step": dom["ms"] / sum(k["ms"] for k in kernels),
-                "note": "the accumulation kernels are bound by shared-memory wavefronts and the "
-                        "integer pipe (pointer doubling), not by HBM; see DESIGN.md 3.3"}
+                "note": "the accumulation kernels are bound on chip (stage A: shared-memory "
+                        "wavefronts of the pointer doubling, 85 % of the pipe), not by HBM; see DESIGN.md 3.3"}
     # the whole step against the same roofline: 14 B/cell (5 D8 + 9 accumulation)
     path_gbs = rows * cols * 14 / (ms * 1e-3) / 1e9
     path_roofline = {"algorithmic_bytes_per_cell": 14, "achieved": path_gbs, "peak": peak,

@@ -1418,12 +1418,13 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
 // are promoted to the X side.  K3 adds 64-bit values as two words with the carry handed
 // on.  Exact, so the result equals the flat resolve bit for bit.
 // ---------------------------------------------------------------------------
-constexpr int SG = 8;                       // tiles per super-tile edge
-constexpr int SUP_THREADS = 1024;
+constexpr int SGX = 8, SGY = 4;             // tiles per super-tile (columns, rows)
+constexpr int SUP_NT = SGX * SGY;
 constexpr int SUP_CPT = 16;                 // nodes per thread
-constexpr int SUP_MAXN = SG * SG * SLOTS;   // 16 384 = SUP_THREADS * SUP_CPT
+constexpr int SUP_MAXN = SUP_NT * SLOTS;    // every slot of every tile a node: always fits
+constexpr int SUP_THREADS = SUP_MAXN / SUP_CPT;
 constexpr int S1_BIG_BITS = 20;             // own values from 2^20 on (and marked ones) go the X way
-static_assert(SUP_MAXN == SUP_THREADS * SUP_CPT, "one pass over a full super-tile");
+static_assert(SUP_NT <= 64 && SUP_THREADS <= 1024, "super-tile size");
 
 struct SupArgs {
     int tiles_x, tiles_y, sup_x;
@@ -1443,8 +1444,8 @@ struct SupArgs {
 constexpr int SUP_SM_PTR = 0;                        // K1 pointer entries / K3 next node
 constexpr int SUP_SM_V0 = SUP_SM_PTR + SUP_MAXN * 4; // K1 packed sums / K3 low words
 constexpr int SUP_SM_V1 = SUP_SM_V0 + SUP_MAXN * 4;  // K3 high words
-constexpr int SUP_SM_TAB = SUP_SM_V1 + SUP_MAXN * 4; // int[65] prefix, int[64] first
-constexpr int SUP_SM_TOTAL = SUP_SM_TAB + 130 * 4;
+constexpr int SUP_SM_TAB = SUP_SM_V1 + SUP_MAXN * 4; // int[SUP_NT + 1] prefix, int[SUP_NT] first
+constexpr int SUP_SM_TOTAL = SUP_SM_TAB + (2 * SUP_NT + 2) * 4;
 
 // K1's rounds: cnt_hand_on / cnt_publish with this kernel's delta between entry and sum
 __device__ __forceinline__ void sup_hand_on(unsigned &low, unsigned a)
@@ -1476,21 +1477,21 @@ __device__ __forceinline__ unsigned sup_publish(unsigned own_addr, unsigned low)
 }
 
 template <int PHASE>
-__global__ void __launch_bounds__(SUP_THREADS, 1)
+__global__ void __launch_bounds__(SUP_THREADS, 65536 / (SUP_THREADS * 64))
 super_tile_kernel(const SupArgs p)
 {
     extern __shared__ __align__(16) unsigned char sup_sm[];
     uint32_t *sptr = reinterpret_cast<uint32_t *>(sup_sm + SUP_SM_PTR);
     uint32_t *sv0 = reinterpret_cast<uint32_t *>(sup_sm + SUP_SM_V0);
     uint32_t *sv1 = reinterpret_cast<uint32_t *>(sup_sm + SUP_SM_V1);
-    int *tpre = reinterpret_cast<int *>(sup_sm + SUP_SM_TAB); // [65]
-    int *tfirst = tpre + 65;                                   // [64]
+    int *tpre = reinterpret_cast<int *>(sup_sm + SUP_SM_TAB); // [SUP_NT + 1]
+    int *tfirst = tpre + SUP_NT + 1;                           // [SUP_NT]
     const int tid = threadIdx.x;
     const int gx = blockIdx.x % p.sup_x, gy = blockIdx.x / p.sup_x;
 
     // ---- the super-tile's tiles and their entries in the node list
-    if (tid < SG * SG) {
-        const int ty = gy * SG + tid / SG, tx = gx * SG + tid % SG;
+    if (tid < SUP_NT) {
+        const int ty = gy * SGY + tid / SGX, tx = gx * SGX + tid % SGX;
         int cnt = 0, first = 0;
         if (ty < p.tiles_y && tx < p.tiles_x) {
             const int t = ty * p.tiles_x + tx;
@@ -1504,19 +1505,21 @@ super_tile_kernel(const SupArgs p)
     if (tid == 0) {
         int run = 0;
         tpre[0] = 0;
-        for (int j = 1; j <= SG * SG; j++) {
+        for (int j = 1; j <= SUP_NT; j++) {
             run += tpre[j];
             tpre[j] = run;
         }
     }
     __syncthreads();
-    const int nG = tpre[SG * SG];
+    const int nG = tpre[SUP_NT];
     if (nG == 0)
         return;
     auto slot_of_index = [&](int i) -> int32_t {
-        int lo = 0, hi = SG * SG; // largest j with tpre[j] <= i
+        int lo = 0, hi = SUP_NT; // largest j with tpre[j] <= i
 #pragma unroll
-        for (int it = 0; it < 6; it++) {
+        for (int it = 0; it < 6; it++) { // 2^6 >= SUP_NT
+            if (hi - lo <= 1)
+                break;
             const int mid = (lo + hi) >> 1;
             if (tpre[mid] <= i)
                 lo = mid;
@@ -1529,7 +1532,7 @@ super_tile_kernel(const SupArgs p)
         if (nx < 0 || nx >= p.ntile_slots)
             return false;
         const int tile = nx / SLOTS, ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        return ty / SG == gy && tx / SG == gx;
+        return ty / SGY == gy && tx / SGX == gx;
     };
 
     int32_t slot[SUP_CPT];
@@ -2121,13 +2124,20 @@ int resolve_two_level(Workspace &wk, int64_t rows, int64_t cols, int want_roots,
                       cudaStream_t st)
 {
     const int tiles_x = ht::cdiv(cols, T), tiles_y = ht::cdiv(rows, T);
-    const int sup_x = ht::cdiv(tiles_x, SG), sup_y = ht::cdiv(tiles_y, SG);
+    const int sup_x = ht::cdiv(tiles_x, SGX), sup_y = ht::cdiv(tiles_y, SGY);
     const int last_h = (int)(rows - (int64_t)(tiles_y - 1) * T);
     HT_CUDA_TRY(cudaMemsetAsync(wk.outer, 0, wk.nslots, st));
     HT_CUDA_TRY(cudaMemsetAsync(wk.base2, 0, wk.nslots * 8, st));
-    HT_CUDA_TRY(cudaMemsetAsync(wk.next2, 0xFF, wk.nslots * 4, st));
-    if (want_roots)
-        HT_CUDA_TRY(cudaMemsetAsync(wk.root1, 0xFF, wk.nslots * 4, st));
+    // next2 / root1 = -1 where K1 does not write them: the virtual slots, and (row bands) the
+    // slots of the first / last tile row that are not nodes
+    const int64_t nts = (int64_t)tiles_x * tiles_y * SLOTS, row_slots = (int64_t)tiles_x * SLOTS;
+    HT_CUDA_TRY(cudaMemsetAsync(wk.next2 + nts, 0xFF, (wk.nslots - nts) * 4, st));
+    if (want_roots) {
+        HT_CUDA_TRY(cudaMemsetAsync(wk.next2, 0xFF, row_slots * 4, st));
+        HT_CUDA_TRY(cudaMemsetAsync(wk.next2 + nts - row_slots, 0xFF, row_slots * 4, st));
+        HT_CUDA_TRY(cudaMemsetAsync(wk.root1, 0xFF, row_slots * 4, st));
+        HT_CUDA_TRY(cudaMemsetAsync(wk.root1 + nts - row_slots, 0xFF, row_slots * 4, st));
+    }
     SupArgs a;
     a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.sup_x = sup_x;
     a.ntile_slots = tiles_x * tiles_y * SLOTS;
@@ -2307,7 +2317,7 @@ extern "C" int ht_acc_resolve(int64_t rows, int64_t cols, int mode, int want_roo
     if (mode != W_F32) {
         const int choice = stage_b_choice();
         const int64_t ntiles = (int64_t)ht::cdiv(cols, T) * ety;
-        if (choice == 2 || (choice == 0 && ntiles >= SG * SG))
+        if (choice == 2 || (choice == 0 && ntiles >= 4 * SUP_NT))
             return resolve_two_level(wk, rows, cols, want_roots, rounds_dev, (cudaStream_t)stream);
     }
     if (mode == W_F32)

@@ -754,6 +754,11 @@ class CudaBand:
                 fn()
             e1.record()
             torch.cuda.synchronize()
-            out.append({"name": name, "ms": e0.elapsed_time(e1) / iters})
+            row = {"name": name, "ms": e0.elapsed_time(e1) / iters}
+            if name == "coarse_resolve_kernel":
+                row["launches"] = ("stage B = ht_acc_resolve: super_tile_kernel<1>, virtual_nodes_kernel, "
+                                   "outer_nodes_kernel, coarse_resolve_kernel on the outer nodes, "
+                                   "super_tile_kernel<3> (two-level resolve, DESIGN.md 3.3)")
+            out.append(row)
         self.take_launches()
         return out

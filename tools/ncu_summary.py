@@ -51,6 +51,8 @@ BENCH_NAME = [
     (r"coarse_resolve_kernel<.*i128", "coarse_resolve_kernel<i128>"),
     (r"weight_max", "weight_max_kernel"),
     (r"acc_local", "acc_local_cnt_kernel"),
+    (r"super_tile_kernel<\(int\)1>|super_tile_kernel<1>", "super_tile_kernel<1>"),
+    (r"super_tile_kernel<\(int\)3>|super_tile_kernel<3>", "super_tile_kernel<3>"),
     (r"coarse_resolve", "coarse_resolve_kernel"),
     (r"acc_final", "acc_final_cnt_kernel"),
     (r"terrain_kernel", "terrain_kernel"),
