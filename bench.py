@@ -86,7 +86,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def __enter__(self):
         if self.nv and not os.environ.get("HT_BENCH_NO_CLOCKS"):
@@ -533,15 +533,18 @@ def run_product(args):
     except Exception as exc:  # capture refused on this driver / NCCL: enqueue launch by launch
         print(f"[bench] graph capture failed ({type(exc).__name__}: {exc}); launching step by step",
               file=sys.stderr)
-        step = engine.flow_direction_accumulation
+        def step():
+            engine.flow_direction_accumulation()
         step.release = lambda: None
         step_mode = "launch by launch"
     for _ in range(args.warmup):
         step()
     launches0 = engine.launches
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the NVML poller starts before the barrier: its first queries (slow when 8 ranks ask at
+    # once) are not part of the timed region, the later ones sample it every 4 ms
     with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             step()
@@ -729,7 +732,7 @@ def run_product(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload_config(world),
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "step_mode": step_mode,
             "roofline": roofline, "path_roofline": path_roofline, "kernels": kernels,
             "boundary_graph": {"resolve_rounds": resolve_rounds,
                                "note": "pointer-doubling rounds of stage B until no node is active"},
@@ -800,7 +803,7 @@ def window_filter_bench(peak):
     y, x = np.mgrid[-10:11, -10:11]
     res = []
     for name, k, method in (("3x3 max", np.ones((3, 3), np.uint8), "max"),
-                            ("disc r=10 mean (row prefix sums)", ((x * x + y * y) <= 100).astype(np.uint8), "mean")):
+                            ("disc r=10 mean (run differences of row prefix sums built in shared memory)", ((x * x + y * y) <= 100).astype(np.uint8), "mean")):
         k = np.ascontiguousarray(k)
         code = {"max": 2, "mean": 4}[method]
 
