@@ -1408,7 +1408,8 @@ coarse_resolve_kernel(const V *base0, const int32_t *next0, int64_t n, const int
 //   K1  super_tile_kernel<1>: one CTA per super-tile resolves the internal forest in SHARED
 //       memory (the rounds of stage A on <= 16 K nodes): S1 = subtree sums over internal
 //       links, root1 = last node of the internal path.  A root with an external link hands
-//       S1 to its target (base2) and flags it OUTER; next2[v] = next0[root1(v)].
+//       S1 to its target (base2) and flags it OUTER; the list of outer nodes gets next2[w] =
+//       next0[root1(w)].
 //   K2  the flat resolve on the OUTER nodes only (~8x fewer): X = what arrives from other
 //       super-tiles, in total.
 //   K3  super_tile_kernel<3>: every OUTER node adds its X along its internal path (a walk of
@@ -1434,8 +1435,8 @@ struct SupArgs {
     const unsigned long long *base0;
     uint8_t *outer;
     unsigned long long *base2;
-    int32_t *next2;
-    uint32_t *s1w;
+    int32_t *rnode;              // per node (list position): slot of the last node of its internal path
+    uint32_t *s1w;               // per node (list position): S1
     unsigned long long *agg;     // K3: X of the outer nodes in, inflow of every node out
     int32_t *root1;              // K1, row bands: last node of the internal path, band-edge slots only
     int edge_tiles_x, edge_tiles_y, edge_last_h;
@@ -1514,7 +1515,9 @@ super_tile_kernel(const SupArgs p)
     const int nG = tpre[SUP_NT];
     if (nG == 0)
         return;
-    auto slot_of_index = [&](int i) -> int32_t {
+    // local index -> position in the node list (per-node arrays are indexed by it: the nodes
+    // of a tile are neighbours there, while their slots are spread over the tile's 256)
+    auto node_of_index = [&](int i) -> int {
         int lo = 0, hi = SUP_NT; // largest j with tpre[j] <= i
 #pragma unroll
         for (int it = 0; it < 6; it++) { // 2^6 >= SUP_NT
@@ -1526,7 +1529,7 @@ super_tile_kernel(const SupArgs p)
             else
                 hi = mid;
         }
-        return p.list[tfirst[lo] + (i - tpre[lo])];
+        return tfirst[lo] + (i - tpre[lo]);
     };
     auto internal = [&](int32_t nx) -> bool {
         if (nx < 0 || nx >= p.ntile_slots)
@@ -1535,102 +1538,185 @@ super_tile_kernel(const SupArgs p)
         return ty / SGY == gy && tx / SGX == gx;
     };
 
+    // Global loads are issued in BATCHES of independent, unconditional loads (an index that is
+    // out of range is clamped to node 0 and its result ignored): with a branch around every
+    // load the 16 cells of a thread paid 3 - 4 dependent round trips to L2 / DRAM EACH.  The
+    // loops stop at the super-tile's node count (typically a third of the capacity).
+    constexpr int GB = 4; // cells per batch
     int32_t slot[SUP_CPT];
 #pragma unroll
     for (int k = 0; k < SUP_CPT; k++) {
+        if (k * SUP_THREADS >= nG) { // uniform
+            slot[k] = -1;
+            continue;
+        }
         const int i = tid + k * SUP_THREADS;
-        slot[k] = i < nG ? slot_of_index(i) : -1;
-        if (PHASE == 1 && i < nG)
-            p.idmap[slot[k]] = i;
+        slot[k] = p.list[node_of_index(i < nG ? i : 0)];
+    }
+#pragma unroll
+    for (int k = 0; k < SUP_CPT; k++) {
+        const int i = tid + k * SUP_THREADS;
+        if (i < nG) {
+            if (PHASE == 1) {
+                p.idmap[slot[k]] = i;
+                sv1[i] = (uint32_t)slot[k]; // K1 keeps the slots in shared memory (the path ends look them up)
+            }
+        } else
+            slot[k] = -1;
     }
     __syncthreads(); // idmap of this super-tile's nodes is read by this CTA only
+    const int32_t safe_slot = p.list[node_of_index(0)]; // node 0 exists (nG > 0): a valid slot to clamp to
 
     const unsigned pbase = ht::smem_u32(sptr), own0 = pbase + 4u * (unsigned)tid;
     if (PHASE == 1) {
         unsigned low[SUP_CPT], a[SUP_CPT];
 #pragma unroll
         for (int k = 0; k < SUP_CPT; k++) {
-            const int i = tid + k * SUP_THREADS;
             low[k] = own0 + (unsigned)(k * SUP_THREADS * 4);
             a[k] = 0u;
-            if (i < nG) {
-                const int32_t nx = p.next0[slot[k]];
-                if (internal(nx))
-                    low[k] = (pbase + 4u * (unsigned)p.idmap[nx]) | J_ACTIVE;
+        }
+#pragma unroll
+        for (int k0 = 0; k0 < SUP_CPT; k0 += GB) {
+            if (k0 * SUP_THREADS >= nG)
+                break; // uniform
+            int32_t nx[GB], li[GB];
+            unsigned long long bv[GB];
+#pragma unroll
+            for (int j = 0; j < GB; j++) {
+                const int32_t sl = slot[k0 + j] >= 0 ? slot[k0 + j] : safe_slot;
+                nx[j] = p.next0[sl];
+                bv[j] = p.base0[sl];
+            }
+#pragma unroll
+            for (int j = 0; j < GB; j++) {
+                const bool in = slot[k0 + j] >= 0 && internal(nx[j]);
+                li[j] = p.idmap[in ? nx[j] : safe_slot];
+                if (!in)
+                    li[j] = -1;
+            }
+#pragma unroll
+            for (int j = 0; j < GB; j++) {
+                const int k = k0 + j;
+                if (slot[k] < 0)
+                    continue;
+                if (li[j] >= 0)
+                    low[k] = (pbase + 4u * (unsigned)li[j]) | J_ACTIVE;
                 // a node whose own value is large (flow imported from a neighbour band) or
                 // carries a band-edge mark is PROMOTED: its value joins what arrives from
                 // outside (base2 -> X, exact by linearity), so that K1's sums stay plain
                 // 32-bit counts: <= 2^19 cells of the super-tile and its ring, + 2^10 band-edge
                 // nodes x 2^20
-                const unsigned long long b = p.base0[slot[k]];
-                if (b >= (1ull << S1_BIG_BITS)) {
-                    atomicAdd(p.base2 + slot[k], b);
+                if (bv[j] >= (1ull << S1_BIG_BITS)) {
+                    atomicAdd(p.base2 + slot[k], bv[j]);
                     p.outer[slot[k]] = 1;
                 } else
-                    a[k] = (unsigned)b;
+                    a[k] = (unsigned)bv[j];
             }
+        }
+#pragma unroll
+        for (int k = 0; k < SUP_CPT; k++) {
+            const int i = tid + k * SUP_THREADS;
             sptr[i] = low[k];
             sv0[i] = a[k];
         }
         __syncthreads();
         for (int round = 0; round < 16; round++) {
 #pragma unroll
-            for (int k = 0; k < SUP_CPT; k++)
+            for (int k = 0; k < SUP_CPT; k++) {
+                if (k * SUP_THREADS >= nG)
+                    break; // uniform
                 sup_hand_on(low[k], a[k]);
+            }
             __syncthreads();
             unsigned any = 0;
 #pragma unroll
             for (int k = 0; k < SUP_CPT; k++) {
+                if (k * SUP_THREADS >= nG)
+                    break; // uniform
                 a[k] = sup_publish(own0 + (unsigned)(k * SUP_THREADS * 4), low[k]);
                 any |= low[k];
             }
             if (!__syncthreads_or((int)(any & J_ACTIVE)))
                 break;
         }
-        // a[] = S1 (packed), low[] = the root of the internal path
+        // a[] = S1, low[] = the root of the internal path
 #pragma unroll
-        for (int k = 0; k < SUP_CPT; k++) {
-            const int i = tid + k * SUP_THREADS;
-            if (i >= nG)
-                continue;
-            const int ri = (int)(((low[k] & ~3u) - pbase) >> 2);
-            const int32_t rslot = ri == i ? slot[k] : slot_of_index(ri);
-            const int32_t nxr = p.next0[rslot];
-            p.s1w[slot[k]] = a[k];
-            p.next2[slot[k]] = nxr;
-            if (ri == i && nxr >= 0) {
-                // the end of an internal path with a link out of the super-tile
-                if (a[k])
-                    atomicAdd(p.base2 + nxr, (unsigned long long)a[k]);
-                p.outer[nxr] = 1;
+        for (int k0 = 0; k0 < SUP_CPT; k0 += GB) {
+            if (k0 * SUP_THREADS >= nG)
+                break; // uniform
+            int32_t nxr[GB];
+#pragma unroll
+            for (int j = 0; j < GB; j++) // own link: needed by the path ends only, loaded for all (L2 hits)
+                nxr[j] = p.next0[slot[k0 + j] >= 0 ? slot[k0 + j] : safe_slot];
+#pragma unroll
+            for (int j = 0; j < GB; j++) {
+                const int k = k0 + j, i = tid + k * SUP_THREADS;
+                if (slot[k] < 0)
+                    continue;
+                const int gi = node_of_index(i);
+                const int ri = (int)(((low[k] & ~3u) - pbase) >> 2);
+                const int32_t rslot = (int32_t)sv1[ri];
+                p.s1w[gi] = a[k];
+                p.rnode[gi] = rslot;
+                if (ri == i && nxr[j] >= 0) {
+                    // the end of an internal path with a link out of the super-tile hands S1 on
+                    if (a[k])
+                        atomicAdd(p.base2 + nxr[j], (unsigned long long)a[k]);
+                    p.outer[nxr[j]] = 1;
+                }
+                if (p.root1 && is_band_edge_slot(slot[k], p.edge_tiles_x, p.edge_tiles_y, p.edge_last_h))
+                    p.root1[slot[k]] = rslot;
             }
-            if (p.root1 && is_band_edge_slot(slot[k], p.edge_tiles_x, p.edge_tiles_y, p.edge_last_h))
-                p.root1[slot[k]] = rslot;
         }
     } else {
         // ---- K3: one-hop internal links, S1 as 64-bit words, the outer nodes walk their X down
         int32_t *snext = reinterpret_cast<int32_t *>(sptr);
+        unsigned long long x[SUP_CPT];
 #pragma unroll
-        for (int k = 0; k < SUP_CPT; k++) {
-            const int i = tid + k * SUP_THREADS;
-            if (i >= nG)
-                continue;
-            const int32_t nx = p.next0[slot[k]];
-            snext[i] = internal(nx) ? p.idmap[nx] : -1;
-            sv0[i] = p.s1w[slot[k]];
-            sv1[i] = 0u;
+        for (int k = 0; k < SUP_CPT; k++)
+            x[k] = 0ull;
+#pragma unroll
+        for (int k0 = 0; k0 < SUP_CPT; k0 += GB) {
+            if (k0 * SUP_THREADS >= nG)
+                break; // uniform
+            int32_t nx[GB], li[GB];
+            unsigned s1[GB];
+#pragma unroll
+            for (int j = 0; j < GB; j++) {
+                const int i = tid + (k0 + j) * SUP_THREADS;
+                const int32_t sl = slot[k0 + j] >= 0 ? slot[k0 + j] : safe_slot;
+                nx[j] = p.next0[sl];
+                x[k0 + j] = p.agg[sl]; // X of an outer node; 0 for every other node
+                s1[j] = p.s1w[node_of_index(i < nG ? i : 0)];
+            }
+#pragma unroll
+            for (int j = 0; j < GB; j++) {
+                const bool in = slot[k0 + j] >= 0 && internal(nx[j]);
+                li[j] = p.idmap[in ? nx[j] : safe_slot];
+                if (!in)
+                    li[j] = -1;
+            }
+#pragma unroll
+            for (int j = 0; j < GB; j++) {
+                const int i = tid + (k0 + j) * SUP_THREADS;
+                if (slot[k0 + j] < 0) {
+                    x[k0 + j] = 0ull;
+                    continue;
+                }
+                snext[i] = li[j];
+                sv0[i] = s1[j];
+                sv1[i] = 0u;
+            }
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < SUP_CPT; k++) {
-            const int i = tid + k * SUP_THREADS;
-            if (i >= nG || !p.outer[slot[k]])
+            if (k * SUP_THREADS >= nG)
+                break; // uniform
+            if (!x[k])
                 continue;
-            const unsigned long long x = p.agg[slot[k]];
-            if (!x)
-                continue;
-            for (int cur = i, step = 0; cur >= 0 && step < SUP_MAXN; cur = snext[cur], step++)
-                smem_add64(sv0 + cur, sv1 + cur, (long long)x);
+            for (int cur = tid + k * SUP_THREADS, step = 0; cur >= 0 && step < SUP_MAXN; cur = snext[cur], step++)
+                smem_add64(sv0 + cur, sv1 + cur, (long long)x[k]);
         }
         __syncthreads();
 #pragma unroll
@@ -1657,9 +1743,11 @@ __global__ void virtual_nodes_kernel(const unsigned long long *base0, unsigned l
     }
 }
 
-// the OUTER nodes of the node list, for the level-2 resolve
+// the OUTER nodes of the node list, for the level-2 resolve, and their level-2 links:
+// next2[w] = where the internal path that starts at w leaves its super-tile
 __global__ void outer_nodes_kernel(const uint8_t *outer, const int32_t *list, const int *nlist,
-                                   int32_t *list2, int *nlist2)
+                                   const int32_t *rnode, const int32_t *next0, int32_t ntile_slots,
+                                   int32_t *next2, int32_t *list2, int *nlist2)
 {
     const int na = *nlist;
     const int lane = threadIdx.x & 31;
@@ -1674,15 +1762,17 @@ __global__ void outer_nodes_kernel(const uint8_t *outer, const int32_t *list, co
         if (lane == 0)
             at = atomicAdd(nlist2, __popc(m));
         at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
-        if (in)
+        if (in) {
             list2[at] = u;
+            next2[u] = u < ntile_slots ? next0[rnode[i]] : -1; // a neighbour band's cell ends the path
+        }
     }
 }
 
 // row bands: the last node of the path of every slot of the band's first / last row --
 // root1 (K1) if the internal path ends inside its super-tile, else the level-2 root of the
 // outer node that path hands over to
-__global__ void edge_roots_kernel(int32_t *root_out, const int32_t *root1, const int32_t *next2,
+__global__ void edge_roots_kernel(int32_t *root_out, const int32_t *root1, const int32_t *next0,
                                   const int32_t *rootX, int tiles_x, int tiles_y, int last_h)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1690,8 +1780,8 @@ __global__ void edge_roots_kernel(int32_t *root_out, const int32_t *root1, const
         return;
     const int side = c >= (int64_t)tiles_x * T, cc = (int)(c - (int64_t)side * tiles_x * T);
     const int32_t s = band_edge_slot_of(side, cc / T, cc % T, tiles_x, tiles_y, last_h);
-    const int32_t n2 = next2[s];              // -1: not a node, or its path ends in its super-tile
-    const int32_t r1 = root1[s];              // -1: not a node
+    const int32_t r1 = root1[s];                    // -1: not a node
+    const int32_t n2 = r1 >= 0 ? next0[r1] : -1;    // where its internal path leaves the super-tile
     root_out[s] = n2 >= 0 ? rootX[n2] : (r1 >= 0 ? r1 : s);
 }
 
@@ -1929,7 +2019,7 @@ struct Workspace {
     int *flags, *nlist;
     unsigned *gmax_bits;
     // two-level stage B (count modes)
-    int32_t *tile_first, *tile_cnt, *next2, *idmapX, *rootX, *root1;
+    int32_t *tile_first, *tile_cnt, *next2, *idmapX, *rootX, *root1, *rnode;
     uint32_t *s1w;
     uint8_t *outer;
     int64_t nslots;
@@ -1957,7 +2047,7 @@ size_t workspace_bytes(int64_t rows, int64_t cols, int mode)
         local = align_up((size_t)rows * ((cols + 7) / 8 * 8) * 2);
     size_t hier = 0;
     if (mode != W_F32)
-        hier = 5 * align_up(n * 4) + align_up(n) +
+        hier = 6 * align_up(n * 4) + align_up(n) +
                2 * align_up((size_t)ht::cdiv(rows, T) * ht::cdiv(cols, T) * 4);
     return 6 * align_up(n * vs) + 9 * align_up(n * 4) + align_up(128 * sizeof(int)) + local + hier + 256;
 }
@@ -2000,7 +2090,7 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, int mode, Works
         w.lacc_ld = (cols + 7) / 8 * 8;
         b += align_up((size_t)rows * w.lacc_ld * 2);
     }
-    w.tile_first = w.tile_cnt = w.next2 = w.idmapX = w.rootX = w.root1 = nullptr;
+    w.tile_first = w.tile_cnt = w.next2 = w.idmapX = w.rootX = w.root1 = w.rnode = nullptr;
     w.s1w = nullptr; w.outer = nullptr;
     if (mode != W_F32) {
         const size_t nt = (size_t)ht::cdiv(rows, T) * ht::cdiv(cols, T);
@@ -2009,6 +2099,7 @@ int carve(void *ws, size_t ws_bytes, int64_t rows, int64_t cols, int mode, Works
         w.rootX = (int32_t *)b; b += align_up(n * 4);
         w.root1 = (int32_t *)b; b += align_up(n * 4);
         w.s1w = (uint32_t *)b; b += align_up(n * 4);
+        w.rnode = (int32_t *)b; b += align_up(n * 4);
         w.outer = (uint8_t *)b; b += align_up(n);
         w.tile_first = (int32_t *)b; b += align_up(nt * 4);
         w.tile_cnt = (int32_t *)b; b += align_up(nt * 4);
@@ -2128,13 +2219,9 @@ int resolve_two_level(Workspace &wk, int64_t rows, int64_t cols, int want_roots,
     const int last_h = (int)(rows - (int64_t)(tiles_y - 1) * T);
     HT_CUDA_TRY(cudaMemsetAsync(wk.outer, 0, wk.nslots, st));
     HT_CUDA_TRY(cudaMemsetAsync(wk.base2, 0, wk.nslots * 8, st));
-    // next2 / root1 = -1 where K1 does not write them: the virtual slots, and (row bands) the
-    // slots of the first / last tile row that are not nodes
+    // root1 = -1 for the slots of the first / last tile row that are not nodes (row bands)
     const int64_t nts = (int64_t)tiles_x * tiles_y * SLOTS, row_slots = (int64_t)tiles_x * SLOTS;
-    HT_CUDA_TRY(cudaMemsetAsync(wk.next2 + nts, 0xFF, (wk.nslots - nts) * 4, st));
     if (want_roots) {
-        HT_CUDA_TRY(cudaMemsetAsync(wk.next2, 0xFF, row_slots * 4, st));
-        HT_CUDA_TRY(cudaMemsetAsync(wk.next2 + nts - row_slots, 0xFF, row_slots * 4, st));
         HT_CUDA_TRY(cudaMemsetAsync(wk.root1, 0xFF, row_slots * 4, st));
         HT_CUDA_TRY(cudaMemsetAsync(wk.root1 + nts - row_slots, 0xFF, row_slots * 4, st));
     }
@@ -2146,7 +2233,7 @@ int resolve_two_level(Workspace &wk, int64_t rows, int64_t cols, int want_roots,
     a.base0 = (const unsigned long long *)wk.base0;
     a.outer = wk.outer;
     a.base2 = (unsigned long long *)wk.base2;
-    a.next2 = wk.next2; a.s1w = wk.s1w;
+    a.rnode = wk.rnode; a.s1w = wk.s1w;
     a.agg = (unsigned long long *)wk.aggB;
     a.root1 = want_roots ? wk.root1 : nullptr;
     a.edge_tiles_x = tiles_x; a.edge_tiles_y = tiles_y; a.edge_last_h = last_h;
@@ -2162,7 +2249,8 @@ int resolve_two_level(Workspace &wk, int64_t rows, int64_t cols, int want_roots,
         HT_LAUNCH_CHECK();
     }
     HT_CUDA_TRY(cudaMemsetAsync(wk.nlist2, 0, sizeof(int), st));
-    outer_nodes_kernel<<<ht::kSMs * 4, 256, 0, st>>>(wk.outer, wk.list, wk.nlist, wk.list2, wk.nlist2);
+    outer_nodes_kernel<<<ht::kSMs * 4, 256, 0, st>>>(wk.outer, wk.list, wk.nlist, wk.rnode, wk.next0,
+                                                     a.ntile_slots, wk.next2, wk.list2, wk.nlist2);
     HT_LAUNCH_CHECK();
     int rc = launch_resolve<unsigned long long>(wk.base2, wk.next2, wk.nslots, wk.list2, wk.nlist2, wk.idmapX,
                                                 wk.ptrA, wk.ptrB, wk.aggA, wk.arr0, wk.arr1,
@@ -2173,7 +2261,7 @@ int resolve_two_level(Workspace &wk, int64_t rows, int64_t cols, int want_roots,
     super_tile_kernel<3><<<sup_x * sup_y, SUP_THREADS, SUP_SM_TOTAL, st>>>(a);
     HT_LAUNCH_CHECK();
     if (want_roots) {
-        edge_roots_kernel<<<ht::cdiv(2ll * tiles_x * T, 256), 256, 0, st>>>(wk.rootB, wk.root1, wk.next2, wk.rootX,
+        edge_roots_kernel<<<ht::cdiv(2ll * tiles_x * T, 256), 256, 0, st>>>(wk.rootB, wk.root1, wk.next0, wk.rootX,
                                                                           tiles_x, tiles_y, last_h);
         HT_LAUNCH_CHECK();
     }
