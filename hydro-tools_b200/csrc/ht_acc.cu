@@ -20,6 +20,7 @@
 //     exact integers for counts) and the final GRASS direction codes.
 // Counts are carried as u64 across tiles; weighted sums as fp64.
 // Algorithmic traffic: 1 B/cell read + 8 B/cell written (+4 B/cell weights).
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -2201,12 +2202,14 @@ int launch_resolve(const void *base0, const int32_t *next0, int64_t n, const int
 
 // HT_STAGE_B = flat | two forces one variant of stage B (tests); default: two levels from
 // one full super-tile on
+std::atomic<int> g_stage_b{-1};
 int stage_b_choice()
 {
-    static int choice = -1;
+    int choice = g_stage_b.load();
     if (choice < 0) {
         const char *e = getenv("HT_STAGE_B");
         choice = !e ? 0 : (e[0] == 'f' ? 1 : (e[0] == 't' ? 2 : 0));
+        g_stage_b.store(choice);
     }
     return choice;
 }
@@ -2290,6 +2293,17 @@ int fill_args(AccArgs &p, int64_t rows, int64_t cols, int64_t row0, int64_t tota
 }
 
 } // namespace
+
+// 0 = automatic (two levels from 128 tiles on), 1 = always the flat resolve, 2 = always two
+// levels; returns the previous setting.  Same as the environment variable HT_STAGE_B
+// (flat / two); a test hook -- both variants give identical results.
+extern "C" int ht_acc_stage_b_mode(int mode)
+{
+    const int prev = stage_b_choice();
+    if (mode >= 0 && mode <= 2)
+        g_stage_b.store(mode);
+    return prev;
+}
 
 extern "C" size_t ht_acc_workspace_bytes(int64_t rows, int64_t cols)
 {

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ht_band_graph": [_p, _int, _i64, _int, _p, _p, _p],
     "ht_acc_final": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _i64, _int,
                      _f32, _p, _i64, _p, _i64, _p, C.c_size_t, _p],
+    "ht_acc_stage_b_mode": [_int],
     "ht_acc_tile_phases": [_i64, _i64, _int, _p, C.c_size_t, _p],
     "ht_acc_final_phase": [_p, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _p, _i64, _int,
                            _f32, _p, _i64, _p, _i64, _p, C.c_size_t, _int, _p],

@@ -561,10 +561,9 @@ class CudaBand:
         # count modes from 128 tiles on: the two-level resolve (csrc/ht_acc.cu resolve_two_level:
         # super_tile_kernel<1>, virtual_nodes, outer_nodes, coarse_resolve, super_tile_kernel<3>,
         # + edge_roots with roots); else the one cooperative kernel
-        import os
         tiles = ((self.rows + T - 1) // T) * ((self.cols + T - 1) // T)
-        force = os.environ.get("HT_STAGE_B", "")[:1]
-        two = self._mode != self.N.MODE_WEIGHTED and (force == "t" or (force != "f" and tiles >= 128))
+        force = self.N.lib.ht_acc_stage_b_mode(-1)  # query only: 0 automatic, 1 flat, 2 two levels
+        two = self._mode != self.N.MODE_WEIGHTED and (force == 2 or (force == 0 and tiles >= 128))
         self._launches += (5 + int(bool(want_roots))) if two else 1
 
     def resolve_rounds(self) -> int:

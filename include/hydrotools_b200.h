@@ -214,6 +214,13 @@ int ht_acc_final_phase(const uint8_t *packed, int64_t packed_ld, int64_t rows, i
                        int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
                        double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld, void *ws,
                        size_t ws_bytes, int phase, void *stream);
+/* stage B of the count modes has two variants with identical results: one flat pointer-
+ * doubling resolve over all nodes, or two levels (super-tiles of 8 x 4 tiles resolved in
+ * shared memory, the flat resolve on the nodes that receive flow from another super-tile,
+ * a walk that hands the external inflow down).  mode 0 = automatic (two levels from 128
+ * tiles on), 1 = flat, 2 = two levels; returns the previous mode.  Test hook; the
+ * environment variable HT_STAGE_B = flat | two sets the initial mode. */
+int ht_acc_stage_b_mode(int mode);
 int ht_acc_f64(const uint8_t *packed, int64_t packed_ld, int64_t rows, int64_t cols,
                int mode, const float *w, int64_t w_ld, int has_wnd, float wnd,
                double *acc, int64_t acc_ld, int8_t *dir_out, int64_t dir_ld, void *ws,

@@ -216,3 +216,31 @@ def test_direction_in_parts_equals_whole(hc):
             band.direction()
         outs.append(band.packed.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("cuts", [[0, 300], [0, 2, 100, 101 + 64, 300], [0, 129, 300]])
+def test_stage_b_variants_agree(hc, cuts):
+    """The flat and the two-level boundary-graph resolve (csrc/ht_acc.cu) leave identical
+    directions, counts and signed counts -- forced on a raster far below the size at which
+    the two-level variant is chosen automatically, so that partial super-tiles, bands of two
+    rows, band-edge marks, roots and the delta resolve all go through it."""
+    from hydrotools.cuda import _native as N
+    dem = oracle.synth_dem(11, 300, 520, with_nulls=True, nodata=ND)
+    res = {}
+    prev = N.lib.ht_acc_stage_b_mode(-1)
+    try:
+        for mode in (1, 2):
+            N.lib.ht_acc_stage_b_mode(mode)
+            assert N.lib.ht_acc_stage_b_mode(-1) == mode
+            if len(cuts) == 2:
+                res[mode] = hc.flow_direction_accumulation_arrays(dem, nodata=ND, csx=10.0, csy=10.0,
+                                                                  positive_only=False)
+            else:
+                res[mode] = run_bands(dem, cuts, ND, 10.0, 10.0, delta=True)
+    finally:
+        N.lib.ht_acc_stage_b_mode(prev)
+    np.testing.assert_array_equal(res[1][0], res[2][0])
+    np.testing.assert_array_equal(res[1][1], res[2][1])
+    efd, efa = oracle.rwatershed(dem, ND, 10.0, 10.0, positive_only=len(cuts) > 2)
+    np.testing.assert_array_equal(res[2][0], efd)
+    np.testing.assert_array_equal(res[2][1], efa)
