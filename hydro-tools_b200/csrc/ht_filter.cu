@@ -523,7 +523,11 @@ run_filter_local_kernel(const __grid_constant__ CUtensorMap map, const float *sr
     }
     __syncthreads();
     ht::mbar_wait(&bar, 0);
-    // ---- row prefixes over the C - 1 raw cells of a row: warp -> rows, lane -> K consecutive cells
+    // ---- row prefixes over the C - 1 raw cells of a row: warp -> rows, lane -> K consecutive cells.
+    // +-inf are data (np.nansum gives inf for a window that holds one, NaN for both signs) but
+    // must stay out of the prefix SUMS, or every difference to their right would be inf - inf:
+    // they are counted instead, in the same word as the valid cells (bits 0..11 valid cells,
+    // 12..21 +inf, 22..31 -inf; prefixes are monotone per field, so differences never borrow).
     const int K = (C - 1 + 31) / 32; // <= KU
     bool dirty = false;
     for (int rr = warp; rr < R; rr += 8) {
@@ -537,11 +541,12 @@ run_filter_local_kernel(const __grid_constant__ CUtensorMap map, const float *sr
             if (k < K && cc < C - 1) {
                 f[k] = raw[rr * bw + shift + cc];
                 const bool ok = f[k] == f[k] && !(has_nodata && f[k] == nodata);
+                const bool fin = fabsf(f[k]) <= 3.4028234e38f;
                 if (!ok)
                     f[k] = __int_as_float(0x7fc00000);
-                dirty |= !ok;
-                run += ok ? (double)f[k] : 0.0;
-                cnt += ok ? 1u : 0u;
+                dirty |= !ok || !fin;
+                run += ok && fin ? (double)f[k] : 0.0;
+                cnt += ok ? (fin ? 1u : (f[k] > 0.0f ? 0x1001u : 0x400001u)) : 0u;
             }
         }
         double ws = run;
@@ -567,8 +572,10 @@ run_filter_local_kernel(const __grid_constant__ CUtensorMap map, const float *sr
             const int cc = lane * K + k;
             if (k < K && cc < C - 1) {
                 if (f[k] == f[k]) {
-                    base += (double)f[k];
-                    cbase += 1u;
+                    const bool fin = fabsf(f[k]) <= 3.4028234e38f;
+                    if (fin)
+                        base += (double)f[k];
+                    cbase += fin ? 1u : (f[k] > 0.0f ? 0x1001u : 0x400001u);
                 }
                 sP[rr * C + cc + 1] = base;
                 sC[rr * bw + cc + 1] = cbase;
@@ -617,8 +624,12 @@ run_filter_local_kernel(const __grid_constant__ CUtensorMap map, const float *sr
         if (y >= rows)
             break;
         const float centre = src[y * ld + x];
-        const bool ok = centre == centre && !(has_nodata && centre == nodata) && n[c];
-        out[y * out_ld + x] = ok ? (float)(mean ? sum[c] / (double)n[c] : sum[c]) : __int_as_float(0x7fc00000);
+        const unsigned nv = n[c] & 0xFFFu, np = (n[c] >> 12) & 0x3FFu, nn = n[c] >> 22;
+        const bool ok = centre == centre && !(has_nodata && centre == nodata) && nv;
+        float r = (float)(mean ? sum[c] / (double)nv : sum[c]);
+        if (np | nn) // the window holds +-inf: inf, or NaN for both signs (np.nansum / nanmean)
+            r = (np && nn) ? __int_as_float(0x7fc00000) : __int_as_float(np ? 0x7f800000 : 0xff800000);
+        out[y * out_ld + x] = ok ? r : __int_as_float(0x7fc00000);
     }
 }
 
@@ -744,7 +755,11 @@ extern "C" int ht_window_filter_runs_f32(const float *src, int64_t rows, int64_t
     }
     cudaStream_t st = (cudaStream_t)stream;
     // kernels whose staged block fits shared memory: local prefixes, no pass over the raster
-    if (n_runs <= MAX_LOCAL_RUNS && kw <= 100) {
+    int n_cells = 0;
+    for (int r = 0; r < n_runs; r++)
+        n_cells += hruns[r].b - hruns[r].a + 1;
+    // (the count word of the local kernel has 12 bits for the cells of a window)
+    if (n_runs <= MAX_LOCAL_RUNS && kw <= 100 && n_cells <= 4095) {
         const int i_start = kh / 2, j_start = kw / 2, j_end = kw - 1 - j_start;
         const int hx0a = (j_start + 3) / 4 * 4; // the TMA box starts on a 16-byte boundary
         for (int th = 32; th >= 8; th >>= 1) {

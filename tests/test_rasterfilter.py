@@ -183,3 +183,27 @@ def test_host_kernel_helpers(hc):
     assert _io.infer_nodata("float32") == float(np.finfo("float32").min)
     assert _io.infer_nodata("uint16") == 65535 and _io.infer_nodata("int8") == -128
     assert _io.infer_nodata("bool") is False
+
+
+@pytest.mark.gpu
+def test_gpu_infinite_values_in_disc_sums(hc):
+    """+-inf are data for np.nansum / np.nanmean (interpolate.py:155-160, 205-208): a window
+    that holds +inf gives +inf, both signs give NaN, every other window stays finite -- also
+    in the run-difference kernel, whose prefix sums must not turn into inf - inf."""
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(150, 300)).astype(np.float32)
+    a[40, 100] = np.inf
+    a[40, 180] = -np.inf
+    a[90, 50] = np.inf
+    a[91, 52] = -np.inf
+    a[rng.random(a.shape) < 0.01] = np.nan
+    yy, xx = np.mgrid[-8:9, -8:9]
+    k = (xx * xx + yy * yy) <= 64
+    for meth in ("sum", "mean"):
+        g = hc.window_filter(a, k, meth)
+        with np.errstate(invalid="ignore"):
+            e = orf.raster_filter(a, k, meth)
+        assert np.array_equal(np.isnan(g), np.isnan(e))
+        assert np.array_equal(np.isposinf(g), np.isposinf(e)) and np.array_equal(np.isneginf(g), np.isneginf(e))
+        m = np.isfinite(e)
+        assert np.max(np.abs(g[m] - e[m]) / np.maximum(np.abs(e[m]), 1e-3)) < 1e-6
