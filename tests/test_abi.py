@@ -80,3 +80,26 @@ def test_lazy_arrays_are_materialised():
     out = D.as_2d(Lazy(a))
     assert isinstance(out, np.ndarray) and not isinstance(out, np.ma.MaskedArray)
     assert out.shape == (3, 4) and out[1, 1] == 5
+
+
+def test_pipeline_fails_loudly_without_a_device(hc):
+    import torch
+    with pytest.raises(ValueError):
+        hc.FlowPipeline(0, 8)
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hc.FlowPipeline(8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        list(hc.flow_direction_accumulation_many([np.zeros((8, 8), np.float32)]))
+    assert list(hc.flow_direction_accumulation_many([])) == []
+
+
+def test_stage_b_mode_hook(hc):
+    from hydrotools.cuda import _native
+    prev = _native.lib.ht_acc_stage_b_mode(-1)
+    assert prev in (0, 1, 2)
+    assert _native.lib.ht_acc_stage_b_mode(1) == prev
+    assert _native.lib.ht_acc_stage_b_mode(7) == 1      # out of range: unchanged
+    assert _native.lib.ht_acc_stage_b_mode(prev) == 1
+    assert _native.lib.ht_acc_stage_b_mode(-1) == prev
